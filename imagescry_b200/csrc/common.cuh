@@ -13,14 +13,7 @@
 #include <cstdarg>
 #include <cstdio>
 
-// ----------------------------------------------------------------------------
-// C-ABI status codes (mirrored in include/imagescry_b200.h)
-// ----------------------------------------------------------------------------
-#define ISX_OK 0
-#define ISX_ERR_INVALID_ARG (-1)
-#define ISX_ERR_CUDA (-2)
-#define ISX_ERR_UNSUPPORTED (-3)
-#define ISX_ERR_WORKSPACE (-4)
+#include "imagescry_b200.h"  // status codes, layouts, dtypes, entry-point declarations
 
 namespace isx {
 
@@ -143,18 +136,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Bounded wait: a protocol bug turns into a trap (launch failure reported to the host)
-// instead of a hung GPU.  The bound is ~10 s of polling, far beyond any legitimate wait.
-#ifndef ISX_MBAR_SPIN_LIMIT
-#define ISX_MBAR_SPIN_LIMIT (1u << 28)
+// Bounded wait: a protocol bug turns into a trap (launch failure reported to the host) instead of a
+// hung GPU.  The bound is wall-clock (%globaltimer, checked every 1024 polls): no legitimate wait
+// inside these kernels lasts anywhere near it.
+#ifndef ISX_MBAR_TIMEOUT_NS
+#define ISX_MBAR_TIMEOUT_NS 4000000000ull
 #endif
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > ISX_MBAR_SPIN_LIMIT) {
-      printf("isx: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", blockIdx.x,
-             threadIdx.x, (void*)bar, parity);
-      __trap();
+    if ((++spins & 1023u) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > ISX_MBAR_TIMEOUT_NS) {
+        printf("isx: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n", blockIdx.x,
+               threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }
@@ -299,6 +304,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
         "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
         "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// TMEM -> registers: 32 lanes x 16 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

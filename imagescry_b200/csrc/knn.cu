@@ -1,0 +1,593 @@
+// Stage 3 of the sift path: exhaustive cosine k-NN over a bf16 embedding store.
+//
+//   K0  row_rnorm_kernel   1 / max(||row||, eps) for the store and the queries (HBM-bound pass)
+//   K4  knn_search_kernel  tcgen05 GEMM  S = Q . E^T  (bf16 operands from TMA-filled shared memory,
+//                          fp32 accumulators in TMEM) with the per-query top-k fused into the
+//                          epilogue: the Q x N score matrix never leaves the SM.
+//   K5  topk_merge_kernel  merges partial top-k lists (N-splits of one GPU, or the shards of
+//                          several GPUs after the NCCL all-gather).
+//
+// There is no reference implementation of this stage; semantics follow
+// oracle/oracle.py::cosine_knn: normalize(q) . normalize(e) with F.normalize's eps
+// (/root/reference/src/imagescry/models/embedding.py:74), ordered by (score desc, index asc).
+//
+// K4 structure (one persistent CTA per SM, 256 threads):
+//   warp 0      TMA producer: query tile 128 x 64 and store tile 256 x 64 (bf16, 128B swizzle) per
+//               k-block into a STAGES-deep shared-memory ring
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma 128 x 256 x 16, accumulating a
+//               128 x 256 fp32 tile in one of two TMEM accumulator stages
+//   warp 2      TMEM allocation / deallocation
+//   warps 4-7   epilogue: tcgen05.ld the finished tile (one query row per thread), scale by the
+//               store row's inverse norm, reject everything below the row's running k-th best with
+//               one compare, append the rare survivors to a per-row candidate buffer and prune that
+//               buffer with a warp-cooperative bitonic sort when it fills up.
+// Work decomposition: items = (N-split, 128-query block); a CTA walks items in split-major order so
+// that CTAs running at the same time stream the same store rows and share them through L2.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+
+namespace isx {
+namespace {
+
+constexpr int BM = 128;  // queries per tile  (TMEM lanes)
+constexpr int BN = 256;  // store rows per tile (TMEM columns)
+constexpr int BK = 64;   // bf16 elements per k-block: 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int ACC_STAGES = 2;
+constexpr int kKnnThreads = 256;
+constexpr int kEpilogueWarp0 = 4;
+constexpr int kMaxK = 128;
+constexpr int kSmallK = 16;  // k <= kSmallK keeps candidate buffers in shared memory
+
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+
+struct KnnPlan {
+  int mb;        // 128-query blocks
+  long long nb;  // 256-row store blocks
+  int splits;    // N-splits
+  long long items;
+  int grid;
+};
+
+KnnPlan plan_knn(long long n, int q, int sms) {
+  KnnPlan p;
+  p.mb = (q + BM - 1) / BM;
+  p.nb = (n + BN - 1) / BN;
+  if (p.nb < 1) p.nb = 1;
+  const long long max_s = std::max<long long>(1, std::min<long long>(p.nb, 4096));
+  // fewest splits whose item count fills whole waves of `sms` CTAs to >= 97 %; else the best seen
+  int best_s = 1;
+  double best_eff = -1.0;
+  for (long long s = 1; s <= max_s; ++s) {
+    const long long items = static_cast<long long>(p.mb) * s;
+    const long long waves = (items + sms - 1) / sms;
+    const double eff = static_cast<double>(items) / static_cast<double>(waves * sms);
+    // keep items long enough to amortise the cold start of the running threshold
+    const bool long_enough = (p.nb / s) >= 16 || s == 1;
+    if (!long_enough) break;
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = static_cast<int>(s); }
+    if (eff >= 0.97) break;
+  }
+  p.splits = best_s;
+  p.items = static_cast<long long>(p.mb) * p.splits;
+  p.grid = static_cast<int>(std::min<long long>(sms, p.items));
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: inverse row norms
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+row_rnorm_kernel(const __nv_bfloat16* __restrict__ x, long long n, int d, float eps,
+                 float* __restrict__ rnorm) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n;
+       row += warps) {
+    const __nv_bfloat16* p = x + row * d;
+    float ss = 0.f;
+    if ((d & 7) == 0 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+      for (int i = lane * 8; i < d; i += 256) {
+        const uint4 v = ld_nc_v4(p + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xFFFF0000u);
+          ss = fmaf(lo, lo, ss);
+          ss = fmaf(hi, hi, ss);
+        }
+      }
+    } else {
+      for (int i = lane; i < d; i += 32) {
+        const float v = __bfloat162float(p[i]);
+        ss = fmaf(v, v, ss);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFullMask, ss, o);
+    if (lane == 0) rnorm[row] = 1.0f / fmaxf(sqrtf(ss), eps);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: search
+// ------------------------------------------------------------------------------------------
+struct KnnParams {
+  int q, d, k;
+  long long n;
+  int mb, splits;
+  long long nb, items;
+  long long index_base;
+  const float* store_rnorm;
+  const float* query_rnorm;
+  float* part_scores;  // [splits][q][k]
+  int32_t* part_idx;   // [splits][q][k]
+  uint2* cand_global;  // [grid][BM][CAP] when k > kSmallK
+};
+
+template <int CAP>
+struct KnnSmem {
+  static constexpr int STAGES = (CAP <= 64) ? 3 : 4;
+  static constexpr uint32_t kCandStride = CAP + 1;  // (score, idx) pairs per row incl. padding
+  static constexpr uint32_t kCandBytes = (CAP <= 64) ? BM * kCandStride * 8 : 0;
+  static constexpr uint32_t kAOff = 0;
+  static constexpr uint32_t kBOff = kAOff + STAGES * A_STAGE_BYTES;
+  static constexpr uint32_t kCandOff = kBOff + STAGES * B_STAGE_BYTES;
+  static constexpr uint32_t kRnormOff = kCandOff + kCandBytes;            // [ACC_STAGES][BN] floats
+  static constexpr uint32_t kBarOff = kRnormOff + ACC_STAGES * BN * 4;    // mbarriers
+  static constexpr uint32_t kNumBars = 2 * STAGES + 2 * ACC_STAGES;
+  static constexpr uint32_t kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr uint32_t kTotal = kTmemPtrOff + 16;
+  static constexpr uint32_t kDynamicBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
+};
+
+__device__ __forceinline__ void epilogue_bar_sync() {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// Warp-cooperative prune of one row's candidate buffer: sort, keep the best k, return the new
+// threshold (score of the k-th best, or -inf while fewer than k candidates exist).
+template <int CAP>
+__device__ __forceinline__ void prune_row(uint2* row_buf, int count, int k, float& new_thr,
+                                          int& new_count, float (&s)[CAP / 32], int (&idx)[CAP / 32]) {
+  constexpr int E = CAP / 32;
+  const int lane = static_cast<int>(lane_id());
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    if (i < count) {
+      const uint2 v = row_buf[i];
+      s[e] = __uint_as_float(v.x);
+      idx[e] = static_cast<int>(v.y);
+    } else {
+      s[e] = -INFINITY;
+      idx[e] = INT_MAX;
+    }
+  }
+  warp_sort_desc<E>(s, idx);
+  float kth = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    if (i < k && i < count) row_buf[i] = make_uint2(__float_as_uint(s[e]), static_cast<uint32_t>(idx[e]));
+    const float cand = __shfl_sync(kFullMask, s[e], (k - 1) & 31);
+    if (e == ((k - 1) >> 5)) kth = cand;
+  }
+  new_count = min(count, k);
+  new_thr = (count >= k) ? kth : -INFINITY;
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(kKnnThreads, 1)
+knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
+                  const KnnParams p) {
+  using L = KnnSmem<CAP>;
+  constexpr int STAGES = L::STAGES;
+  constexpr int E = CAP / 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + ACC_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
+  float* rnorm_s = reinterpret_cast<float*>(smem + L::kRnormOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.d + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_e);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int split = static_cast<int>(item / p.mb);
+        const int mblk = static_cast<int>(item - static_cast<long long>(split) * p.mb);
+        const long long nb0 = p.nb * split / p.splits, nb1 = p.nb * (split + 1) / p.splits;
+        for (long long nb = nb0; nb < nb1; ++nb) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+            tma_load_2d(smem + L::kAOff + stage * A_STAGE_BYTES, &tmap_q, &full_bar[stage], kb * BK,
+                        mblk * BM, kEvictLast);
+            tma_load_2d(smem + L::kBOff + stage * B_STAGE_BYTES, &tmap_e, &full_bar[stage], kb * BK,
+                        static_cast<int32_t>(nb * BN), kEvictNormal);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, BM, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int split = static_cast<int>(item / p.mb);
+        const long long nb0 = p.nb * split / p.splits, nb1 = p.nb * (split + 1) / p.splits;
+        for (long long nb = nb0; nb < nb1; ++nb) {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + L::kAOff + stage * A_STAGE_BYTES);
+            const uint32_t b_addr = smem_u32(smem + L::kBOff + stage * B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t a_desc = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 2);
+              const uint64_t b_desc = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2);
+              tc_mma_f16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+            }
+            tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(&tmem_full[acc]);  // accumulator complete
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    // ===================== epilogue: fused top-k =====================
+    const int ew = warp - kEpilogueWarp0;     // == warp % 4: the TMEM lane quarter this warp may read
+    const int row = ew * 32 + lane;           // query row inside the tile
+    const int et = threadIdx.x - kEpilogueWarp0 * 32;  // 0..127
+    uint2* cand_base;
+    uint32_t cand_stride;
+    if (CAP <= 64) {
+      cand_base = reinterpret_cast<uint2*>(smem + L::kCandOff);
+      cand_stride = L::kCandStride;
+    } else {
+      cand_base = p.cand_global + static_cast<size_t>(blockIdx.x) * BM * CAP;
+      cand_stride = CAP;
+    }
+    uint2* my_buf = cand_base + static_cast<size_t>(row) * cand_stride;
+    uint2* warp_buf = cand_base + static_cast<size_t>(ew * 32) * cand_stride;
+
+    uint32_t acc = 0, acc_phase = 0;
+    float s_reg[E];
+    int i_reg[E];
+    for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int split = static_cast<int>(item / p.mb);
+      const int mblk = static_cast<int>(item - static_cast<long long>(split) * p.mb);
+      const long long nb0 = p.nb * split / p.splits, nb1 = p.nb * (split + 1) / p.splits;
+      const int qrow = mblk * BM + row;
+      const bool row_valid = qrow < p.q;
+      float thr = row_valid ? -INFINITY : INFINITY;
+      int cnt = 0;
+
+      for (long long nb = nb0; nb < nb1; ++nb) {
+        const long long n0 = nb * BN;
+        const int ncols = static_cast<int>(min(static_cast<long long>(BN), p.n - n0));
+        // stage the store rows' inverse norms for this tile (the previous user of this slot was
+        // tile nb-2, whose readers all passed the barrier of tile nb-1)
+        float* rn = rnorm_s + acc * BN;
+        rn[et] = (et < ncols) ? __ldg(p.store_rnorm + n0 + et) : 0.f;
+        rn[et + 128] = (et + 128 < ncols) ? __ldg(p.store_rnorm + n0 + et + 128) : 0.f;
+        epilogue_bar_sync();
+
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + chunk * 32, r);
+          tc_wait_ld();
+          const float4* rn4 = reinterpret_cast<const float4*>(rn + chunk * 32);
+          float vmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = rn4[j];
+            const float a = __uint_as_float(r[4 * j + 0]) * w.x;
+            const float b = __uint_as_float(r[4 * j + 1]) * w.y;
+            const float c = __uint_as_float(r[4 * j + 2]) * w.z;
+            const float d = __uint_as_float(r[4 * j + 3]) * w.w;
+            r[4 * j + 0] = __float_as_uint(a);
+            r[4 * j + 1] = __float_as_uint(b);
+            r[4 * j + 2] = __float_as_uint(c);
+            r[4 * j + 3] = __float_as_uint(d);
+            vmax = fmaxf(vmax, fmaxf(fmaxf(a, b), fmaxf(c, d)));
+          }
+          if (vmax > thr) {
+            // rare path: some score in this chunk beats the row's running k-th best
+            const int cbase = chunk * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]);
+              if (v > thr && cbase + j < ncols) {
+                my_buf[cnt] = make_uint2(r[j], static_cast<uint32_t>(n0 + cbase + j));
+                ++cnt;
+              }
+            }
+          }
+          // warp-uniform: prune every row that could overflow during the next chunk
+          uint32_t need = __ballot_sync(kFullMask, cnt > CAP - 32);
+          while (need) {
+            const int rr = __ffs(need) - 1;
+            need &= need - 1;
+            __syncwarp();
+            const int c = __shfl_sync(kFullMask, cnt, rr);
+            float nthr;
+            int ncnt;
+            prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, c, p.k, nthr, ncnt, s_reg, i_reg);
+            __syncwarp();
+            if (lane == rr) { thr = nthr; cnt = ncnt; }
+          }
+        }
+        // release the accumulator stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+
+      // item done: final sort of every row, write this split's partial top-k
+      const float rq_mine = row_valid ? __ldg(p.query_rnorm + qrow) : 0.f;
+      for (int rr = 0; rr < 32; ++rr) {
+        __syncwarp();
+        const int c = __shfl_sync(kFullMask, cnt, rr);
+        const float rq = __shfl_sync(kFullMask, rq_mine, rr);
+        const int qr = mblk * BM + ew * 32 + rr;
+        float nthr;
+        int ncnt;
+        prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, c, p.k, nthr, ncnt, s_reg, i_reg);
+        if (qr < p.q) {
+          float* os = p.part_scores + (static_cast<size_t>(split) * p.q + qr) * p.k;
+          int32_t* oi = p.part_idx + (static_cast<size_t>(split) * p.q + qr) * p.k;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int i = e * 32 + lane;
+            if (i < p.k) {
+              const bool have = i < ncnt;
+              os[i] = have ? s_reg[e] * rq : -INFINITY;
+              oi[i] = have ? static_cast<int32_t>(p.index_base + i_reg[e]) : -1;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: merge g sorted-or-not partial lists per query into the final top-k.  One warp per query.
+// ------------------------------------------------------------------------------------------
+template <int CAP>
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, int g, int q, int k,
+                  float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+  constexpr int E = CAP / 32;
+  const int lane = threadIdx.x & 31;
+  const int query = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (query >= q) return;
+  // registers hold a sorted window of CAP entries; the best `keep` survive each round and the
+  // remaining CAP - keep slots are refilled with fresh candidates
+  const int keep = k;
+  const int fresh = CAP - keep;
+  float s[E];
+  int id[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) { s[e] = -INFINITY; id[e] = INT_MAX; }
+  const long long total = static_cast<long long>(g) * k;
+  for (long long base = 0; base < total; base += fresh) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int pos = e * 32 + lane;
+      if (pos >= keep) {
+        const long long c = base + (pos - keep);
+        float sv = -INFINITY;
+        int iv = INT_MAX;
+        if (c < total) {
+          const long long part = c / k, j = c - part * k;
+          const size_t off = (static_cast<size_t>(part) * q + query) * k + j;
+          const int raw = idx[off];
+          if (raw >= 0) { sv = scores[off]; iv = raw; }
+        }
+        s[e] = sv;
+        id[e] = iv;
+      }
+    }
+    warp_sort_desc<E>(s, id);
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int pos = e * 32 + lane;
+    if (pos < k) {
+      const bool have = id[e] != INT_MAX;
+      out_scores[static_cast<size_t>(query) * k + pos] = have ? s[e] : -INFINITY;
+      out_idx[static_cast<size_t>(query) * k + pos] = have ? id[e] : -1;
+    }
+  }
+}
+
+int launch_merge(const float* scores, const int32_t* idx, int g, int q, int k, float* out_scores,
+                 int32_t* out_idx, cudaStream_t stream) {
+  const int warps_per_block = 4;
+  const int blocks = (q + warps_per_block - 1) / warps_per_block;
+  if (k <= 32)
+    topk_merge_kernel<64><<<blocks, 128, 0, stream>>>(scores, idx, g, q, k, out_scores, out_idx);
+  else
+    topk_merge_kernel<256><<<blocks, 128, 0, stream>>>(scores, idx, g, q, k, out_scores, out_idx);
+  ISX_CHECK_CUDA(cudaGetLastError());
+  return ISX_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct KnnWorkspace {
+  size_t part_scores_off, part_idx_off, cand_off, total;
+};
+
+KnnWorkspace knn_workspace(const KnnPlan& plan, int q, int k) {
+  KnnWorkspace w;
+  size_t off = 0;
+  w.part_scores_off = off;
+  off = align_up(off + static_cast<size_t>(plan.splits) * q * k * sizeof(float), 256);
+  w.part_idx_off = off;
+  off = align_up(off + static_cast<size_t>(plan.splits) * q * k * sizeof(int32_t), 256);
+  w.cand_off = off;
+  if (k > kSmallK) off = align_up(off + static_cast<size_t>(plan.grid) * BM * 256 * sizeof(uint2), 256);
+  w.total = off + 256;
+  return w;
+}
+
+template <int CAP>
+int launch_search(const CUtensorMap& tq, const CUtensorMap& te, const KnnParams& p, int grid, cudaStream_t stream) {
+  auto kern = knn_search_kernel<CAP>;
+  const int smem = static_cast<int>(KnnSmem<CAP>::kDynamicBytes);
+  ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, kKnnThreads, smem, stream>>>(tq, te, p);
+  ISX_CHECK_CUDA(cudaGetLastError());
+  return ISX_OK;
+}
+
+}  // namespace
+}  // namespace isx
+
+using namespace isx;
+
+extern "C" {
+
+int isx_row_rnorm_bf16(const void* x, int64_t n, int d, float eps, float* rnorm, isx_stream_t stream_) {
+  const char* fn = "isx_row_rnorm_bf16";
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ISX_REQUIRE(n >= 0 && d > 0, "%s: need n >= 0 and d > 0 (n=%lld d=%d)", fn, (long long)n, d);
+  if (n == 0) return ISX_OK;
+  ISX_REQUIRE(x && rnorm, "%s: null pointer", fn);
+  int sms = 148;
+  int rc = device_sm_count(&sms);
+  if (rc != ISX_OK) return rc;
+  const long long want = (n + 7) / 8;
+  const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(sms) * 16)));
+  row_rnorm_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), n, d, eps, rnorm);
+  ISX_CHECK_CUDA(cudaGetLastError());
+  return ISX_OK;
+}
+
+size_t isx_knn_workspace_bytes(int64_t n, int q, int d, int k) {
+  (void)d;
+  if (n <= 0 || q <= 0 || k <= 0 || k > kMaxK) return 0;
+  int sms = 148;
+  if (device_sm_count(&sms) != ISX_OK) sms = 148;
+  const KnnPlan plan = plan_knn(n, q, sms);
+  return knn_workspace(plan, q, k).total;
+}
+
+int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const void* queries,
+                   const float* query_rnorm, int q, int d, int k, int64_t index_base,
+                   float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes,
+                   isx_stream_t stream_) {
+  const char* fn = "isx_knn_search";
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ISX_REQUIRE(q > 0 && d > 0 && k > 0 && n >= 0, "%s: need q, d, k > 0 and n >= 0 (q=%d d=%d k=%d n=%lld)", fn, q, d, k, (long long)n);
+  ISX_REQUIRE(k <= kMaxK, "%s: k = %d exceeds the supported maximum of %d", fn, k, kMaxK);
+  ISX_REQUIRE(d % 8 == 0, "%s: d = %d must be a multiple of 8 (16-byte rows for TMA)", fn, d);
+  ISX_REQUIRE(n < (1ll << 31) - BN, "%s: at most 2^31 store rows per call (n=%lld); shard the store", fn, (long long)n);
+  ISX_REQUIRE(index_base >= 0 && index_base + n < (1ll << 31), "%s: index_base + n must fit in int32", fn);
+  ISX_REQUIRE(queries && query_rnorm && out_scores && out_idx, "%s: null pointer", fn);
+  ISX_REQUIRE((reinterpret_cast<uintptr_t>(queries) & 15u) == 0 && (reinterpret_cast<uintptr_t>(store) & 15u) == 0,
+              "%s: store and queries must be 16-byte aligned", fn);
+  if (n == 0) {
+    // nothing to search: the merge of zero lists writes (-inf, -1) everywhere
+    return launch_merge(out_scores, out_idx, 0, q, k, out_scores, out_idx, stream);
+  }
+  ISX_REQUIRE(store && store_rnorm, "%s: null store pointer", fn);
+  int sms = 148;
+  int rc = device_sm_count(&sms);
+  if (rc != ISX_OK) return rc;
+  const KnnPlan plan = plan_knn(n, q, sms);
+  const KnnWorkspace ws = knn_workspace(plan, q, k);
+  ISX_REQUIRE(workspace != nullptr && workspace_bytes >= ws.total, "%s: workspace too small (%zu < %zu)", fn,
+              workspace_bytes, ws.total);
+  uint8_t* wbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+
+  CUtensorMap tq, te;
+  rc = encode_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, queries, static_cast<uint64_t>(q),
+                      static_cast<uint64_t>(d), static_cast<uint64_t>(d) * 2, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != ISX_OK) return rc;
+  rc = encode_tmap_2d(&te, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, store, static_cast<uint64_t>(n),
+                      static_cast<uint64_t>(d), static_cast<uint64_t>(d) * 2, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != ISX_OK) return rc;
+
+  KnnParams p;
+  p.q = q; p.d = d; p.k = k; p.n = n;
+  p.mb = plan.mb; p.splits = plan.splits; p.nb = plan.nb; p.items = plan.items;
+  p.index_base = index_base;
+  p.store_rnorm = store_rnorm;
+  p.query_rnorm = query_rnorm;
+  p.part_scores = reinterpret_cast<float*>(wbase + ws.part_scores_off);
+  p.part_idx = reinterpret_cast<int32_t*>(wbase + ws.part_idx_off);
+  p.cand_global = reinterpret_cast<uint2*>(wbase + ws.cand_off);
+
+  if (k <= kSmallK) rc = launch_search<64>(tq, te, p, plan.grid, stream);
+  else rc = launch_search<256>(tq, te, p, plan.grid, stream);
+  if (rc != ISX_OK) return rc;
+  return launch_merge(p.part_scores, p.part_idx, plan.splits, q, k, out_scores, out_idx, stream);
+}
+
+int isx_topk_merge(const float* scores, const int32_t* idx, int g, int q, int k, float* out_scores,
+                   int32_t* out_idx, isx_stream_t stream_) {
+  const char* fn = "isx_topk_merge";
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ISX_REQUIRE(g >= 0 && q > 0 && k > 0, "%s: need g >= 0, q > 0, k > 0 (g=%d q=%d k=%d)", fn, g, q, k);
+  ISX_REQUIRE(k <= kMaxK, "%s: k = %d exceeds the supported maximum of %d", fn, k, kMaxK);
+  ISX_REQUIRE(out_scores && out_idx && (g == 0 || (scores && idx)), "%s: null pointer", fn);
+  return launch_merge(scores, idx, g, q, k, out_scores, out_idx, stream);
+}
+
+}  // extern "C"

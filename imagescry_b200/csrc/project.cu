@@ -1,0 +1,562 @@
+// Stage 2 of the sift path: L2-normalise (+ spatial mean pool) + PCA projection, fused.
+//
+// Replaces, behind the C ABI in include/imagescry_b200.h,
+//   /root/reference/src/imagescry/models/embedding.py:74       F.normalize(x, p=2, dim=1)
+//   /root/reference/src/imagescry/data.py:112-118              EmbeddingBatch.get_flat_vectors
+//   /root/reference/src/imagescry/models/decomposition.py:79-91 PCA.forward: (x - mean) @ components
+//   /root/reference/src/imagescry/models/pipelines.py:82-84    reshape(B,h,w,k).permute(0,3,1,2)
+//
+// K3  l2norm_project_kernel (per-cell mode): the fp32 B x E x h x w feature map is read ONCE.
+//   out[cell, :] = rnorm[cell] * (x[cell, :] . W) + bias,   bias = -(mean . W),
+//   rnorm[cell] = 1 / max(||x[cell, :]||, 1e-12)
+// which equals (x/||x|| - mean) . W.  The contraction runs on tcgen05 tensor cores with fp32-class
+// accuracy: x and W are split into bf16 hi + lo parts and three MMAs (hi.hi + lo.hi + hi.lo)
+// accumulate into the same fp32 TMEM tile (error ~2^-16 relative per product, far inside the 1e-3
+// tolerance; a single bf16 or tf32 pass is not).
+//
+//   warp 0       TMA producer for the packed weight tiles (W_hi, W_lo; bf16, K-major, 128B swizzle)
+//   warp 1       MMA issuer (one elected lane)
+//   warp 2       TMEM allocation
+//   warps 4-7    epilogue: tcgen05.ld, scale by the cell's inverse norm, add bias, store rows of `out`
+//   warps 8-15   transform: coalesced fp32 loads of the NCHW map (cells are the contiguous dim, so a
+//                warp reads 128 contiguous bytes per channel), accumulate the per-cell sum of squares,
+//                split to bf16 hi/lo and write K-major swizzled operand tiles for the MMA.
+//
+// K3p l2norm_pool_kernel (pool mode): one pass over the map with 16-cell slabs staged in shared
+// memory by cp.async; per image the spatial mean of the normalised cells comes out as E floats,
+// which then go through the same projection kernel as an n x F matrix (normalize = 0).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace isx {
+namespace {
+
+constexpr int PM = 128;  // cells per tile (TMEM lanes)
+constexpr int PK = 64;   // features per k-block
+constexpr int P_UMMA_K = 16;
+constexpr int kProjThreads = 512;
+constexpr int kTransformWarp0 = 8;
+constexpr int kTransformThreads = 256;
+constexpr int kMaxComponents = 256;
+
+constexpr uint32_t A_PART_BYTES = PM * PK * 2;           // 16 KB (one of hi / lo)
+constexpr uint32_t A_STAGE_BYTES_P = 2 * A_PART_BYTES;   // hi + lo
+constexpr uint32_t W_PART_BYTES = kMaxComponents * PK * 2;  // 32 KB
+constexpr uint32_t W_STAGE_BYTES = 2 * W_PART_BYTES;
+constexpr int A_STAGES = 2, W_STAGES = 2, P_ACC_STAGES = 2;
+
+struct ProjSmem {
+  static constexpr uint32_t kAOff = 0;
+  static constexpr uint32_t kWOff = kAOff + A_STAGES * A_STAGE_BYTES_P;      // 64 KB
+  static constexpr uint32_t kSsOff = kWOff + W_STAGES * W_STAGE_BYTES;       // +128 KB
+  static constexpr uint32_t kBiasOff = kSsOff + P_ACC_STAGES * 2 * PM * 4;   // [acc][half][row]
+  static constexpr uint32_t kBarOff = kBiasOff + kMaxComponents * 4;
+  static constexpr uint32_t kNumBars = 2 * A_STAGES + 2 * W_STAGES + 4 * P_ACC_STAGES;
+  static constexpr uint32_t kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr uint32_t kTotal = kTmemPtrOff + 16;
+  static constexpr uint32_t kDynamicBytes = kTotal + 1024;
+};
+
+struct PackedLayout {
+  int k_pad, f_pad;
+  size_t hi_off, lo_off, bias_off, total;
+};
+
+PackedLayout packed_layout(int F, int k) {
+  PackedLayout l;
+  l.k_pad = (k + 15) / 16 * 16;
+  l.f_pad = (F + PK - 1) / PK * PK;
+  const size_t mat = static_cast<size_t>(l.k_pad) * l.f_pad * 2;
+  l.hi_off = 0;
+  l.lo_off = (mat + 255) / 256 * 256;
+  l.bias_off = l.lo_off + (mat + 255) / 256 * 256;
+  l.total = l.bias_off + (static_cast<size_t>(l.k_pad) * 4 + 255) / 256 * 256;
+  return l;
+}
+
+// One warp per component j: split every weight into bf16 hi + lo and accumulate the bias in fp64.
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ means, const float* __restrict__ comps, int F, int k,
+                    long long ld_f, long long ld_k, int k_pad, int f_pad, __nv_bfloat16* __restrict__ w_hi,
+                    __nv_bfloat16* __restrict__ w_lo, float* __restrict__ bias) {
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= k_pad) return;
+  double acc = 0.0;
+  for (int f = lane; f < f_pad; f += 32) {
+    float w = 0.f;
+    if (j < k && f < F) {
+      w = comps[f * ld_f + j * ld_k];
+      acc += static_cast<double>(means[f]) * static_cast<double>(w);
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    w_hi[static_cast<size_t>(j) * f_pad + f] = hi;
+    w_lo[static_cast<size_t>(j) * f_pad + f] = lo;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+  if (lane == 0) bias[j] = static_cast<float>(-acc);
+}
+
+struct ProjParams {
+  const float* fmap;
+  long long m_total;  // B * hw cells (rows)
+  int E, hw, k, k_pad;
+  int normalize;
+  long long tiles;
+  const float* bias;
+  float* out;
+};
+
+__device__ __forceinline__ uint32_t bf16_hi_lo(float x, uint32_t& lo_bits) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+  lo_bits = static_cast<uint32_t>(__bfloat16_as_ushort(lo));
+  return static_cast<uint32_t>(__bfloat16_as_ushort(hi));
+}
+
+__global__ void __launch_bounds__(kProjThreads, 1)
+l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_constant__ CUtensorMap tmap_wlo,
+                      const ProjParams p) {
+  using L = ProjSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* a_full = bars;                        // [A_STAGES]  count 256 (transform threads)
+  uint64_t* a_empty = a_full + A_STAGES;          // [A_STAGES]  tcgen05.commit
+  uint64_t* w_full = a_empty + A_STAGES;          // [W_STAGES]  TMA
+  uint64_t* w_empty = w_full + W_STAGES;          // [W_STAGES]  tcgen05.commit
+  uint64_t* tmem_full = w_empty + W_STAGES;       // [ACC]       tcgen05.commit
+  uint64_t* tmem_empty = tmem_full + P_ACC_STAGES;  // [ACC]     4 epilogue warps
+  uint64_t* ss_full = tmem_empty + P_ACC_STAGES;  // [ACC]       256 transform threads
+  uint64_t* ss_empty = ss_full + P_ACC_STAGES;    // [ACC]       4 epilogue warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
+  float* ss_s = reinterpret_cast<float*>(smem + L::kSsOff);
+  float* bias_s = reinterpret_cast<float*>(smem + L::kBiasOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.E + PK - 1) / PK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_whi);
+    prefetch_tmap(&tmap_wlo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], kTransformThreads); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < P_ACC_STAGES; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&ss_full[i], kTransformThreads);
+      mbar_init(&ss_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kMaxComponents; i += blockDim.x) bias_s[i] = (i < p.k_pad) ? p.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t w_part_bytes = static_cast<uint32_t>(p.k_pad) * PK * 2;
+
+  if (warp == 0) {
+    // ===================== weight TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&w_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&w_full[stage], 2 * w_part_bytes);
+          uint8_t* dst = smem + L::kWOff + stage * W_STAGE_BYTES;
+          tma_load_2d(dst, &tmap_whi, &w_full[stage], kb * PK, 0, kEvictLast);
+          tma_load_2d(dst + W_PART_BYTES, &tmap_wlo, &w_full[stage], kb * PK, 0, kEvictLast);
+          if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(/*bf16*/ 1, PM, static_cast<uint32_t>(p.k_pad));
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, acc = 0, acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kMaxComponents;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&w_full[ws], wph);
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + L::kAOff + as * A_STAGE_BYTES_P);
+          const uint32_t a_lo = a_hi + A_PART_BYTES;
+          const uint32_t w_hi = smem_u32(smem + L::kWOff + ws * W_STAGE_BYTES);
+          const uint32_t w_lo = w_hi + W_PART_BYTES;
+#pragma unroll
+          for (int k = 0; k < PK / P_UMMA_K; ++k) {
+            const uint32_t o = k * P_UMMA_K * 2;
+            const uint64_t dah = make_kmajor_sw128_desc(a_hi + o), dal = make_kmajor_sw128_desc(a_lo + o);
+            const uint64_t dwh = make_kmajor_sw128_desc(w_hi + o), dwl = make_kmajor_sw128_desc(w_lo + o);
+            tc_mma_f16(d_tmem, dah, dwh, idesc, (kb | k) != 0);
+            tc_mma_f16(d_tmem, dal, dwh, idesc, 1);
+            tc_mma_f16(d_tmem, dah, dwl, idesc, 1);
+          }
+          tc_commit(&a_empty[as]);
+          tc_commit(&w_empty[ws]);
+          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+        }
+        tc_commit(&tmem_full[acc]);
+        if (++acc == P_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= kTransformWarp0) {
+    // ===================== transform: fp32 NCHW -> bf16 hi/lo K-major tiles =====================
+    const int t = threadIdx.x - kTransformWarp0 * 32;  // 0..255
+    const int m = t & (PM - 1);                        // row (cell) inside the tile
+    const int half = t >> 7;                           // which 32 of the k-block's 64 features
+    const long long my_tiles = (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const long long total_seq = my_tiles * num_kb;
+
+    auto row_base = [&](long long tile_iter, bool& valid) -> const float* {
+      const long long tile = blockIdx.x + tile_iter * gridDim.x;
+      const long long R = tile * PM + m;
+      valid = R < p.m_total;
+      const long long img = valid ? R / p.hw : 0;
+      const long long cell = valid ? R - img * p.hw : 0;
+      return p.fmap + img * p.E * static_cast<long long>(p.hw) + cell;
+    };
+    auto load_block = [&](float (&x)[32], long long seq) {
+      const long long tile_iter = seq / num_kb;
+      const int kb = static_cast<int>(seq - tile_iter * num_kb);
+      bool valid;
+      const float* base = row_base(tile_iter, valid);
+      const int f0 = kb * PK + half * 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int f = f0 + i;
+        x[i] = (valid && f < p.E) ? __ldg(base + static_cast<long long>(f) * p.hw) : 0.f;
+      }
+    };
+
+    float ss = 0.f;
+    uint32_t acc = 0, acc_phase = 0;
+    auto process = [&](float (&x)[32], long long seq) {
+      const uint32_t stage = static_cast<uint32_t>(seq & 1);
+      const uint32_t phase = static_cast<uint32_t>((seq >> 1) & 1);
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = x[2 * i], b = x[2 * i + 1];
+        ss = fmaf(a, a, ss);
+        ss = fmaf(b, b, ss);
+        uint32_t la, lb;
+        const uint32_t ha = bf16_hi_lo(a, la), hb = bf16_hi_lo(b, lb);
+        hi[i] = ha | (hb << 16);
+        lo[i] = la | (lb << 16);
+      }
+      mbar_wait(&a_empty[stage], phase ^ 1);
+      uint8_t* a_hi = smem + L::kAOff + stage * A_STAGE_BYTES_P + m * 128;
+      uint8_t* a_lo = a_hi + A_PART_BYTES;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int chunk = (half * 4 + c) ^ (m & 7);  // 128B swizzle: 16-byte chunk index XOR row % 8
+        *reinterpret_cast<uint4*>(a_hi + chunk * 16) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        *reinterpret_cast<uint4*>(a_lo + chunk * 16) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+      mbar_arrive(&a_full[stage]);
+      const long long tile_iter = seq / num_kb;
+      if (seq - tile_iter * num_kb == num_kb - 1) {
+        // last k-block of the tile: publish this thread's share of the row's sum of squares
+        mbar_wait(&ss_empty[acc], acc_phase ^ 1);
+        ss_s[(acc * 2 + half) * PM + m] = ss;
+        mbar_arrive(&ss_full[acc]);
+        ss = 0.f;
+        if (++acc == P_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    };
+
+    float xa[32], xb[32];
+    if (total_seq > 0) load_block(xa, 0);
+    for (long long seq = 0; seq < total_seq; seq += 2) {
+      if (seq + 1 < total_seq) load_block(xb, seq + 1);
+      process(xa, seq);
+      if (seq + 1 < total_seq) {
+        if (seq + 2 < total_seq) load_block(xa, seq + 2);
+        process(xb, seq + 1);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter
+    const int row = ew * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    const bool vec_ok = (p.k & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0;
+    for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      const long long R = tile * PM + row;
+      mbar_wait(&ss_full[acc], acc_phase);
+      float rn = 1.0f;
+      if (p.normalize) {
+        const float ssum = ss_s[(acc * 2 + 0) * PM + row] + ss_s[(acc * 2 + 1) * PM + row];
+        rn = 1.0f / fmaxf(sqrtf(ssum), 1e-12f);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ss_empty[acc]);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kMaxComponents;
+      float* orow = p.out + R * p.k;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.k_pad; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(taddr + c0, r);
+        tc_wait_ld();
+        if (R < p.m_total) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), rn, bias_s[c0 + j]);
+          if (vec_ok && c0 + 16 <= p.k) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(orow + c0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.k) orow[c0 + j] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == P_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3p: pooled[b][e] = (1/hw) * sum_cells x[b][e][cell] * rnorm[b][cell]  — one pass over the map.
+// One CTA per image at a time; 16-cell slabs [E][16] double-buffered in shared memory via cp.async.
+// ------------------------------------------------------------------------------------------
+constexpr int kSlabCells = 16;
+constexpr int kPoolThreads = 256;
+constexpr int kPoolMaxAcc = 24;  // channels per thread: E <= 64 * 24 = 1536
+
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kPoolThreads)
+l2norm_pool_kernel(const float* __restrict__ fmap, int B, int E, int hw, float* __restrict__ pooled) {
+  extern __shared__ __align__(16) uint8_t pool_smem[];
+  float* slab[2] = {reinterpret_cast<float*>(pool_smem),
+                    reinterpret_cast<float*>(pool_smem) + static_cast<size_t>(E) * kSlabCells};
+  __shared__ float part[16][kSlabCells];
+  __shared__ float rn_s[kSlabCells];
+  const int t = threadIdx.x;
+  const int nslab = (hw + kSlabCells - 1) / kSlabCells;
+  const bool vec = (hw & 3) == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15u) == 0;
+
+  auto issue = [&](int b, int s, float* dst) {
+    const float* src = fmap + static_cast<long long>(b) * E * hw + s * kSlabCells;
+    const int cells = min(kSlabCells, hw - s * kSlabCells);
+    if (vec) {
+      // hw % 4 == 0: whole 16-byte quads are either inside the image row or outside
+      for (int i = t; i < E * 4; i += kPoolThreads) {
+        const int e = i >> 2, qd = i & 3;
+        float* d = dst + e * kSlabCells + qd * 4;
+        if (qd * 4 < cells) cp_async_16(d, src + static_cast<long long>(e) * hw + qd * 4);
+        else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      for (int i = t; i < E * kSlabCells; i += kPoolThreads) {
+        const int e = i >> 4, c = i & 15;
+        float* d = dst + e * kSlabCells + c;
+        if (c < cells) cp_async_4(d, src + static_cast<long long>(e) * hw + c);
+        else *d = 0.f;
+      }
+    }
+    cp_async_commit();
+  };
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float acc[kPoolMaxAcc];
+#pragma unroll
+    for (int i = 0; i < kPoolMaxAcc; ++i) acc[i] = 0.f;
+    issue(b, 0, slab[0]);
+    for (int s = 0; s < nslab; ++s) {
+      float* cur = slab[s & 1];
+      if (s + 1 < nslab) { issue(b, s + 1, slab[(s + 1) & 1]); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncthreads();
+      // per-cell sum of squares: thread = (cell, part), 16 parts stride over the channels
+      {
+        const int cell = t & 15, prt = t >> 4;
+        float ssq = 0.f;
+        for (int e = prt; e < E; e += 16) {
+          const float v = cur[e * kSlabCells + cell];
+          ssq = fmaf(v, v, ssq);
+        }
+        part[prt][cell] = ssq;
+      }
+      __syncthreads();
+      if (t < kSlabCells) {
+        float ssq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ssq += part[i][t];
+        const bool live = s * kSlabCells + t < hw;
+        rn_s[t] = live ? 1.0f / fmaxf(sqrtf(ssq), 1e-12f) : 0.f;
+      }
+      __syncthreads();
+      // weighted channel sums: thread = (channel group, quarter of the 16 cells)
+      {
+        const int qd = t & 3;
+        const float4 w = *reinterpret_cast<const float4*>(&rn_s[qd * 4]);
+#pragma unroll
+        for (int i = 0; i < kPoolMaxAcc; ++i) {
+          const int e = (t >> 2) + 64 * i;
+          if (e < E) {
+            const float4 v = *reinterpret_cast<const float4*>(cur + e * kSlabCells + qd * 4);
+            acc[i] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[i]))));
+          }
+        }
+      }
+      __syncthreads();  // everyone is done with `cur` before it is refilled two slabs later
+    }
+    const float inv = 1.0f / static_cast<float>(hw);
+#pragma unroll
+    for (int i = 0; i < kPoolMaxAcc; ++i) {
+      float v = acc[i];
+      v += __shfl_xor_sync(kFullMask, v, 1);
+      v += __shfl_xor_sync(kFullMask, v, 2);
+      const int e = (t >> 2) + 64 * i;
+      if ((t & 3) == 0 && e < E) pooled[static_cast<long long>(b) * E + e] = v * inv;
+    }
+  }
+}
+
+int launch_project(const float* fmap, long long m_total, int E, int hw, int k, int normalize,
+                   const void* packed, float* out, cudaStream_t stream, const char* fn) {
+  const PackedLayout l = packed_layout(E, k);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  CUtensorMap twh, twl;
+  int rc = encode_tmap_2d(&twh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pk + l.hi_off, static_cast<uint64_t>(l.k_pad),
+                          static_cast<uint64_t>(l.f_pad), static_cast<uint64_t>(l.f_pad) * 2,
+                          static_cast<uint32_t>(l.k_pad), PK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != ISX_OK) return rc;
+  rc = encode_tmap_2d(&twl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pk + l.lo_off, static_cast<uint64_t>(l.k_pad),
+                      static_cast<uint64_t>(l.f_pad), static_cast<uint64_t>(l.f_pad) * 2,
+                      static_cast<uint32_t>(l.k_pad), PK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != ISX_OK) return rc;
+  int sms = 148;
+  rc = device_sm_count(&sms);
+  if (rc != ISX_OK) return rc;
+  ProjParams p;
+  p.fmap = fmap; p.m_total = m_total; p.E = E; p.hw = hw; p.k = k; p.k_pad = l.k_pad;
+  p.normalize = normalize;
+  p.tiles = (m_total + PM - 1) / PM;
+  p.bias = reinterpret_cast<const float*>(pk + l.bias_off);
+  p.out = out;
+  (void)fn;
+  const int grid = static_cast<int>(std::min<long long>(sms, p.tiles));
+  const int smem = static_cast<int>(ProjSmem::kDynamicBytes);
+  ISX_CHECK_CUDA(cudaFuncSetAttribute(l2norm_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  l2norm_project_kernel<<<grid, kProjThreads, smem, stream>>>(twh, twl, p);
+  ISX_CHECK_CUDA(cudaGetLastError());
+  return ISX_OK;
+}
+
+}  // namespace
+}  // namespace isx
+
+using namespace isx;
+
+extern "C" {
+
+size_t isx_project_packed_bytes(int F, int k) {
+  if (F <= 0 || k <= 0 || k > kMaxComponents) return 0;
+  return packed_layout(F, k).total;
+}
+
+int isx_project_pack(const float* feature_means, const float* comps, int F, int k, int64_t ld_f,
+                     int64_t ld_k, void* packed, size_t packed_bytes, isx_stream_t stream_) {
+  const char* fn = "isx_project_pack";
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ISX_REQUIRE(F > 0 && k > 0, "%s: need F > 0 and k > 0 (F=%d k=%d)", fn, F, k);
+  ISX_REQUIRE(k <= kMaxComponents, "%s: at most %d components are supported (k=%d)", fn, kMaxComponents, k);
+  ISX_REQUIRE(feature_means && comps && packed, "%s: null pointer", fn);
+  const PackedLayout l = packed_layout(F, k);
+  ISX_REQUIRE(packed_bytes >= l.total, "%s: packed buffer too small (%zu < %zu)", fn, packed_bytes, l.total);
+  ISX_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "%s: packed buffer must be 256-byte aligned", fn);
+  uint8_t* pk = static_cast<uint8_t*>(packed);
+  const int warps_per_block = 8;
+  const int blocks = (l.k_pad + warps_per_block - 1) / warps_per_block;
+  pack_weights_kernel<<<blocks, 256, 0, stream>>>(feature_means, comps, F, k, ld_f, ld_k, l.k_pad, l.f_pad,
+                                                  reinterpret_cast<__nv_bfloat16*>(pk + l.hi_off),
+                                                  reinterpret_cast<__nv_bfloat16*>(pk + l.lo_off),
+                                                  reinterpret_cast<float*>(pk + l.bias_off));
+  ISX_CHECK_CUDA(cudaGetLastError());
+  return ISX_OK;
+}
+
+size_t isx_l2norm_project_workspace_bytes(int B, int E, int h, int w, int k, int pool) {
+  (void)h; (void)w; (void)k;
+  if (!pool || B <= 0 || E <= 0) return 256;
+  return static_cast<size_t>(B) * E * sizeof(float) + 256;  // pooled B x E vectors
+}
+
+int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, int normalize,
+                       const void* packed, int k, float* out, void* workspace, size_t workspace_bytes,
+                       isx_stream_t stream_) {
+  const char* fn = "isx_l2norm_project";
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ISX_REQUIRE(B > 0 && E > 0 && h > 0 && w > 0 && k > 0, "%s: dimensions must be positive (B=%d E=%d h=%d w=%d k=%d)",
+              fn, B, E, h, w, k);
+  ISX_REQUIRE(k <= kMaxComponents, "%s: at most %d components are supported (k=%d)", fn, kMaxComponents, k);
+  ISX_REQUIRE(fmap && packed && out, "%s: null pointer", fn);
+  ISX_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "%s: packed buffer must be 256-byte aligned", fn);
+  const long long hw = static_cast<long long>(h) * w;
+  ISX_REQUIRE(hw < (1ll << 24) && static_cast<long long>(B) * hw < (1ll << 40), "%s: feature map too large", fn);
+  if (!pool) {
+    return launch_project(fmap, static_cast<long long>(B) * hw, E, static_cast<int>(hw), k, normalize, packed, out,
+                          stream, fn);
+  }
+  ISX_REQUIRE(normalize, "%s: pool == 1 requires normalize == 1", fn);
+  ISX_REQUIRE(E <= 64 * kPoolMaxAcc, "%s: pooled mode supports at most %d channels (E=%d)", fn, 64 * kPoolMaxAcc, E);
+  const size_t need = isx_l2norm_project_workspace_bytes(B, E, h, w, k, 1);
+  ISX_REQUIRE(workspace && workspace_bytes >= need, "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, need);
+  float* pooled = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  int sms = 148;
+  int rc = device_sm_count(&sms);
+  if (rc != ISX_OK) return rc;
+  const size_t smem = static_cast<size_t>(2) * E * kSlabCells * sizeof(float);
+  ISX_CHECK_CUDA(cudaFuncSetAttribute(l2norm_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int per_sm = std::max<int>(1, static_cast<int>((220 * 1024) / (smem + 2048)));
+  const int grid = std::min(B, sms * per_sm);
+  l2norm_pool_kernel<<<grid, kPoolThreads, smem, stream>>>(fmap, B, E, static_cast<int>(hw), pooled);
+  ISX_CHECK_CUDA(cudaGetLastError());
+  // project the pooled rows: an n x F matrix is a feature "map" with one cell per image
+  return launch_project(pooled, B, E, 1, k, /*normalize=*/0, packed, out, stream, fn);
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+"""PCA — drop-in for `imagescry/models/decomposition.py`, projection computed on tcgen05.
+
+`PCA.forward` / `PCA.transform` (`decomposition.py:79-91,150-165`) run the fused sm_100a projection
+kernel (`isx_l2norm_project` with `normalize=0`); `project_feature_map` exposes the fully fused
+L2-normalise (+pool) + projection of a backbone feature map.  `fit` (`:94-148`) is the reference's
+algorithm on torch (offline, not on the hot path — SURVEY.md §8f).
+
+The reference derives from `LightningModule`; lightning is not part of this image, so the base is
+`torch.nn.Module` with the same hyper-parameter surface (`hparams`, `save_hyperparameters`).
+"""
+
+from __future__ import annotations
+
+import torch
+from jaxtyping import Float, jaxtyped
+from torch import Tensor, nn
+
+from imagescry_b200 import _lib
+from imagescry_b200.typechecking import typechecker
+
+
+class _HParams(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+class HParamsModule(nn.Module):
+    """nn.Module with the slice of LightningModule's hyper-parameter API the reference uses."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self._hparams = _HParams()
+
+    def save_hyperparameters(self, hp: dict | None = None) -> None:
+        if hp:
+            self._hparams.update(dict(hp))
+
+    @property
+    def hparams(self) -> _HParams:
+        return self._hparams
+
+
+class PCA(HParamsModule):
+    """Principal component analysis: linear projection to a lower dimensional space via SVD."""
+
+    def __init__(
+        self,
+        *,
+        min_num_components: int = 1,
+        max_num_components: int | None = None,
+        min_explained_variance: float = 0.0,
+        num_features: int = 0,
+        num_components: int = 0,
+    ) -> None:
+        super().__init__()
+        if min_num_components < 1:
+            raise ValueError(f"min_num_components must be at least 1, got {min_num_components}")
+        if max_num_components is not None and max_num_components < min_num_components:
+            raise ValueError(f"max_num_components must be at least {min_num_components}, got {max_num_components}")
+        if min_explained_variance < 0.0 or min_explained_variance > 1.0:
+            raise ValueError(f"min_explained_variance must be between 0.0 and 1.0, got {min_explained_variance}")
+
+        self.min_num_components = min_num_components
+        self.max_num_components = max_num_components
+        self.min_explained_variance = min_explained_variance
+        self.save_hyperparameters({
+            "min_num_components": min_num_components,
+            "max_num_components": max_num_components,
+            "min_explained_variance": min_explained_variance,
+        })
+
+        self._fitted = nn.Parameter(torch.tensor(False), requires_grad=False)
+        self._num_features = nn.Parameter(torch.tensor(0), requires_grad=False)
+        self._num_components = nn.Parameter(torch.tensor(0), requires_grad=False)
+        self.feature_means = nn.Parameter(torch.empty((1, num_features)), requires_grad=False)
+        self.explained_variance = nn.Parameter(torch.empty((num_features,)), requires_grad=False)
+        self.component_vectors = nn.Parameter(torch.empty((num_features, num_components)), requires_grad=False)
+        self._packed: Tensor | None = None
+        self._packed_key: tuple | None = None
+
+    def __repr__(self) -> str:
+        num_features = self.num_features if self.fitted else "not fitted"
+        num_components = self.num_components if self.fitted else "not fitted"
+        return f"{self.__class__.__name__}(num_features={num_features}, num_components={num_components})"
+
+    # ------------------------------------------------------------------ packed weights
+    def packed_weights(self) -> Tensor:
+        """bf16 hi/lo split of `component_vectors` plus the bias -(means . components), in the layout
+        the projection kernel's TMA descriptors read.  Rebuilt when the parameters change."""
+        cv, fm = self.component_vectors, self.feature_means
+        _lib.require_cuda(cv, "PCA parameters")
+        key = (cv.data_ptr(), fm.data_ptr(), cv._version, fm._version, tuple(cv.shape), tuple(cv.stride()), str(cv.device))
+        if self._packed is None or self._packed_key != key:
+            lib = _lib.load()
+            F, k = cv.shape
+            nbytes = lib.isx_project_packed_bytes(F, k)
+            if nbytes == 0:
+                raise ValueError(f"PCA projection kernel supports 1..256 components, got {k} (features={F})")
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=cv.device)
+            means = fm.detach().reshape(-1).contiguous().float()
+            comps = cv.detach().float()
+            rc = lib.isx_project_pack(
+                means.data_ptr(), comps.data_ptr(), F, k, comps.stride(0), comps.stride(1), packed.data_ptr(), nbytes,
+                _lib.stream_ptr(cv.device),
+            )
+            _lib.check(rc, "isx_project_pack")
+            self._packed, self._packed_key = packed, key
+        return self._packed
+
+    # ------------------------------------------------------------------ projection
+    @jaxtyped(typechecker=typechecker)
+    def forward(
+        self, x: Float[Tensor, "num_samples {self.num_features}"]
+    ) -> Float[Tensor, "num_samples {self.num_components}"]:
+        """Project the input data: `(x - feature_means) @ component_vectors` (`decomposition.py:91`)."""
+        _lib.require_cuda(x, "x")
+        n, F = x.shape
+        k = self.num_components
+        out = torch.empty((n, k), dtype=torch.float32, device=x.device)
+        if n == 0:
+            return out
+        xf = x.float().contiguous()
+        lib = _lib.load()
+        rc = lib.isx_l2norm_project(
+            xf.data_ptr(), n, F, 1, 1, 0, 0, self.packed_weights().data_ptr(), k, out.data_ptr(), None, 0,
+            _lib.stream_ptr(x.device),
+        )
+        _lib.check(rc, "isx_l2norm_project")
+        return out
+
+    def project_feature_map(self, fmap: Float[Tensor, "B E H W"], *, pool: str | None = None) -> Tensor:
+        """Fused stage 2 on a backbone feature map: L2-normalise every cell over the channels
+        (`embedding.py:74`), optionally mean-pool the cells, project (`decomposition.py:91`).
+
+        pool=None  → B×k×h×w with NHWC strides, the exact tensor `pipelines.py:82-84` returns.
+        pool="mean" → B×k.
+        """
+        if not self.fitted:
+            raise RuntimeError("PCA model not fitted")
+        _lib.require_cuda(fmap, "fmap")
+        if pool not in (None, "mean"):
+            raise ValueError(f"Invalid pool: {pool}")
+        B, E, h, w = fmap.shape
+        if E != self.num_features:
+            raise ValueError(f"feature map has {E} channels, PCA was fitted on {self.num_features}")
+        k = self.num_components
+        f = fmap.float().contiguous()
+        lib = _lib.load()
+        if pool is None:
+            out = torch.empty((B, h, w, k), dtype=torch.float32, device=f.device)
+            ws, ws_bytes = None, 0
+        else:
+            out = torch.empty((B, k), dtype=torch.float32, device=f.device)
+            ws_bytes = lib.isx_l2norm_project_workspace_bytes(B, E, h, w, k, 1)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=f.device)
+        if B > 0:
+            rc = lib.isx_l2norm_project(
+                f.data_ptr(), B, E, h, w, int(pool is not None), 1, self.packed_weights().data_ptr(), k,
+                out.data_ptr(), None if ws is None else ws.data_ptr(), ws_bytes, _lib.stream_ptr(f.device),
+            )
+            _lib.check(rc, "isx_l2norm_project")
+        return out.permute(0, 3, 1, 2) if pool is None else out
+
+    # ------------------------------------------------------------------ fit (offline)
+    @jaxtyped(typechecker=typechecker)
+    def fit(self, x: Float[Tensor, "num_samples num_features"]) -> "PCA":
+        """Fit by SVD of the centred data (`decomposition.py:94-148`): same component selection
+        rule (min/max components, minimum explained variance).  Runs on x's device with torch."""
+        num_samples, num_features = x.shape
+        if num_samples < 2:
+            raise ValueError(f"num_samples must be at least 2, got {num_samples}")
+        self._num_features = nn.Parameter(torch.tensor(num_features), requires_grad=False)
+        self.feature_means = nn.Parameter(x.mean(dim=0, keepdim=True), requires_grad=False)
+        x_centered = x - self.feature_means
+        # Only the singular values and right singular vectors are used; the reduced SVD yields the
+        # same `s` and `vt` as the reference's full one without the num_samples² `U`.
+        _, s, vt = torch.linalg.svd(x_centered, full_matrices=False)
+        if vt.shape[0] < num_features:  # fewer samples than features: pad like the full SVD's shapes
+            s = torch.cat([s, s.new_zeros(num_features - s.shape[0])])
+        eigenvalues = s**2 / (num_samples - 1)
+        total_variance = torch.sum(eigenvalues)
+        self.explained_variance = nn.Parameter(eigenvalues / total_variance, requires_grad=False)
+        cumulative = torch.cumsum(self.explained_variance, dim=0)
+        need = int(torch.sum(cumulative < self.min_explained_variance).item() + 1)
+        num_components = max(self.min_num_components, need)
+        if self.max_num_components is not None:
+            num_components = min(self.max_num_components, num_components)
+        num_components = min(num_components, vt.shape[0])
+        self._num_components = nn.Parameter(torch.tensor(num_components), requires_grad=False)
+        self.component_vectors = nn.Parameter(vt[:num_components, :].T, requires_grad=False)
+        self._fitted = nn.Parameter(torch.tensor(True), requires_grad=False)
+        self.hparams.update({"num_features": num_features, "num_components": num_components})
+        self._packed = None
+        return self
+
+    @jaxtyped(typechecker=typechecker)
+    def transform(self, x: Float[Tensor, "num_samples num_features"]) -> Float[Tensor, "num_samples num_components"]:
+        """Project the input data (`decomposition.py:150-165`).
+
+        Raises:
+            RuntimeError: If the PCA model is not fitted.
+        """
+        if not self.fitted:
+            raise RuntimeError("PCA model not fitted")
+        return self(x)
+
+    @property
+    def fitted(self) -> bool:
+        return bool(self._fitted.item())
+
+    @property
+    def num_features(self) -> int:
+        return int(self._num_features.item())
+
+    @property
+    def num_components(self) -> int:
+        return int(self._num_components.item())

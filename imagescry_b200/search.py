@@ -1,0 +1,187 @@
+"""Exhaustive cosine k-NN over a bf16 embedding store (stage 3 of the sift path).
+
+The reference has no search entry point; this module adds one on top of what its
+store holds (`storage/models.py:94-129`: float32 C×H×W BLOBs → rows of a bf16 matrix).  Semantics:
+`normalize(q) @ normalize(e).T` with `F.normalize`'s eps (`models/embedding.py:74`), top-k ordered by
+(score descending, index ascending).
+
+Single GPU:   EmbeddingStore(embeddings).search(queries, k)
+Several GPUs: ShardedEmbeddingStore — rows are split contiguously over the ranks of a
+              `torch.distributed` group (one process per GPU); every rank searches its shard with the
+              fused tcgen05 kernel, one all-gather of (score, index) pairs follows, and every rank
+              merges the gathered lists.  Preprocessing and projection shard by batch and need no
+              collective.
+"""
+
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from imagescry_b200 import _lib
+
+MAX_K = 128
+
+
+def shard_range(num_rows: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous row range [begin, end) owned by `rank`: sizes differ by at most one row."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f"invalid rank {rank} for world size {world_size}")
+    base, rem = divmod(num_rows, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def row_rnorm(x: Tensor, eps: float = 1e-12) -> Tensor:
+    """fp32 `1 / max(||row||, eps)` of a bf16 matrix (the denominator of `F.normalize`)."""
+    _lib.require_cuda(x, "x")
+    if x.dtype != torch.bfloat16 or x.ndim != 2 or not x.is_contiguous():
+        raise ValueError("row_rnorm expects a contiguous 2-D bfloat16 tensor")
+    n, d = x.shape
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    if n:
+        rc = _lib.load().isx_row_rnorm_bf16(x.data_ptr(), n, d, eps, out.data_ptr(), _lib.stream_ptr(x.device))
+        _lib.check(rc, "isx_row_rnorm_bf16")
+    return out
+
+
+def merge_topk(scores: Tensor, indices: Tensor, k: int | None = None) -> tuple[Tensor, Tensor]:
+    """Merge G partial results (G×Q×k fp32 scores, G×Q×k int32 indices; index < 0 = padding) into
+    Q×k, ordered by (score desc, index asc)."""
+    _lib.require_cuda(scores, "scores")
+    if scores.shape != indices.shape or scores.ndim != 3:
+        raise ValueError("scores and indices must both be G×Q×k")
+    g, q, kk = scores.shape
+    k = kk if k is None else k
+    if k != kk:
+        raise ValueError(f"k={k} does not match the partial lists' width {kk}")
+    s = scores.contiguous().float()
+    i = indices.contiguous().to(torch.int32)
+    out_s = torch.empty((q, k), dtype=torch.float32, device=s.device)
+    out_i = torch.empty((q, k), dtype=torch.int32, device=s.device)
+    if q:
+        rc = _lib.load().isx_topk_merge(
+            s.data_ptr(), i.data_ptr(), g, q, k, out_s.data_ptr(), out_i.data_ptr(), _lib.stream_ptr(s.device)
+        )
+        _lib.check(rc, "isx_topk_merge")
+    return out_s, out_i
+
+
+def _as_bf16_matrix(x: Tensor, name: str) -> Tensor:
+    _lib.require_cuda(x, name)
+    if x.ndim != 2:
+        raise ValueError(f"{name} must be 2-D (rows × features), got shape {tuple(x.shape)}")
+    if not x.dtype.is_floating_point:
+        raise ValueError(f"{name} must be a floating-point tensor, got {x.dtype}")
+    return x.to(torch.bfloat16).contiguous()
+
+
+class EmbeddingStore:
+    """A device-resident N×d bf16 embedding matrix with its inverse row norms.
+
+    Vectors are kept as given (not re-rounded after normalisation): the kernel multiplies bf16×bf16
+    products exactly, accumulates in fp32 and applies both inverse norms in the epilogue."""
+
+    def __init__(self, embeddings: Tensor, *, index_base: int = 0) -> None:
+        self.embeddings = _as_bf16_matrix(embeddings, "embeddings")
+        self.index_base = int(index_base)
+        self.rnorm = row_rnorm(self.embeddings)
+        self._workspace: Tensor | None = None
+
+    def __len__(self) -> int:
+        return self.embeddings.shape[0]
+
+    @property
+    def dim(self) -> int:
+        return self.embeddings.shape[1]
+
+    @property
+    def device(self) -> torch.device:
+        return self.embeddings.device
+
+    def _ws(self, nbytes: int) -> Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def search_raw(self, queries: Tensor, k: int, *, query_rnorm: Tensor | None = None) -> tuple[Tensor, Tensor]:
+        """Local top-k: fp32 scores Q×k and int32 global indices Q×k (padding: -inf / -1)."""
+        q = _as_bf16_matrix(queries, "queries")
+        if q.shape[1] != self.dim:
+            raise ValueError(f"queries have {q.shape[1]} features, the store has {self.dim}")
+        if not (1 <= k <= MAX_K):
+            raise ValueError(f"k must be between 1 and {MAX_K}, got {k}")
+        if q.device != self.device:
+            raise ValueError(f"queries are on {q.device}, the store is on {self.device}")
+        nq = q.shape[0]
+        scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        idx = torch.empty((nq, k), dtype=torch.int32, device=self.device)
+        if nq == 0:
+            return scores, idx
+        qr = row_rnorm(q) if query_rnorm is None else query_rnorm
+        lib = _lib.load()
+        n = len(self)
+        ws_bytes = max(int(lib.isx_knn_workspace_bytes(n, nq, self.dim, k)), 256)
+        ws = self._ws(ws_bytes)
+        rc = lib.isx_knn_search(
+            self.embeddings.data_ptr(), self.rnorm.data_ptr(), n, q.data_ptr(), qr.data_ptr(), nq, self.dim, k,
+            self.index_base, scores.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(),
+            _lib.stream_ptr(self.device),
+        )
+        _lib.check(rc, "isx_knn_search")
+        return scores, idx
+
+    def search(self, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
+        """Cosine top-k of every query row: (scores fp32 Q×k, indices int64 Q×k)."""
+        scores, idx = self.search_raw(queries, k)
+        return scores, idx.to(torch.int64)
+
+
+def knn_search(embeddings: Tensor, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
+    """One-shot convenience: build an `EmbeddingStore` and search it."""
+    return EmbeddingStore(embeddings).search(queries, k)
+
+
+def gather_partials(scores: Tensor, idx: Tensor, group=None) -> tuple[Tensor, Tensor]:
+    """All-gather every rank's local top-k: returns (G×Q×k scores, G×Q×k indices).  The only
+    collective of the sift path; backend-agnostic (NCCL over NVLink on GPUs, gloo in CPU tests)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    q, k = scores.shape
+    # concatenation along dim 0 is the one output form every backend (NCCL, gloo) accepts
+    all_s = torch.empty((world * q, k), dtype=scores.dtype, device=scores.device)
+    all_i = torch.empty((world * q, k), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(all_s, scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, idx.contiguous(), group=group)
+    return all_s.view(world, q, k), all_i.view(world, q, k)
+
+
+class ShardedEmbeddingStore:
+    """Row-sharded store over the ranks of a process group (one process per GPU).
+
+    `local_embeddings` are this rank's rows; their global indices start at `index_base` (by default
+    the contiguous partition of `shard_range`).  Queries are replicated on every rank."""
+
+    def __init__(self, local_embeddings: Tensor, *, total_rows: int | None = None, index_base: int | None = None, group=None) -> None:
+        import torch.distributed as dist
+
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if index_base is None:
+            if total_rows is None:
+                raise ValueError("give either index_base or total_rows")
+            begin, end = shard_range(total_rows, self.world_size, self.rank)
+            if end - begin != local_embeddings.shape[0]:
+                raise ValueError(
+                    f"rank {self.rank} should hold rows [{begin}, {end}) but got {local_embeddings.shape[0]} rows"
+                )
+            index_base = begin
+        self.local = EmbeddingStore(local_embeddings, index_base=index_base)
+
+    def search(self, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
+        scores, idx = self.local.search_raw(queries, k)
+        all_s, all_i = gather_partials(scores, idx, self.group)
+        s, i = merge_topk(all_s, all_i, k)
+        return s, i.to(torch.int64)

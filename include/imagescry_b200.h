@@ -1,0 +1,143 @@
+/*
+ * imagescry_b200 — C ABI of the B200-native sift path (libimagescry_b200.so).
+ *
+ * The reference (libertininick/imagescry) is pure Python and has no FFI layer; its seams on this
+ * path are Python callables.  Each entry point below replaces the arithmetic behind
+ * one of those seams and is what a ctypes binding in the reference would call (INTEGRATION.md shows
+ * the stubs).  Citations are /root/reference/src/imagescry/<file>:<line>.
+ *
+ * Conventions
+ *   - every pointer except `workspace`-free host out-params is a DEVICE pointer on the current device;
+ *   - all functions are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream), re-entrant, and own no device memory: the caller allocates outputs and
+ *     workspaces (sizes from the *_workspace_bytes functions);
+ *   - return value: ISX_OK, or a negative code with a per-thread message from isx_last_error();
+ *   - no function reads or writes host copies of the data; there is no CPU fallback.
+ */
+#ifndef IMAGESCRY_B200_H_
+#define IMAGESCRY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISX_ABI_VERSION 1
+
+/* status codes */
+#define ISX_OK 0
+#define ISX_ERR_INVALID_ARG (-1)
+#define ISX_ERR_CUDA (-2)
+#define ISX_ERR_UNSUPPORTED (-3)
+#define ISX_ERR_WORKSPACE (-4)
+
+/* tile layouts */
+#define ISX_LAYOUT_NCHW 0 /* planar: what ImageBatch.images holds (data.py:29-41)          */
+#define ISX_LAYOUT_NHWC 1 /* interleaved: what a decoder / PIL hands over (image/io.py:41-52) */
+
+/* element types */
+#define ISX_DTYPE_U8 0
+#define ISX_DTYPE_F32 1
+#define ISX_DTYPE_BF16 2
+
+typedef void* isx_stream_t;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int isx_abi_version(void);
+const char* isx_last_error(void);
+/* SM count and compute capability of the current device (host out-params). */
+int isx_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- stage 1: tile preprocessing ------------------------------------------------------------
+ * Replaces image/transforms.py:78-126 `resize` (bilinear, align_corners=False, no antialias),
+ * image/transforms.py:16-74 `normalize_per_channel` and their composition
+ * models/embedding.py:150-165 `EfficientNetEmbedder.preprocess`, plus the HWC->CHW step of
+ * image/io.py:52 / data.py:456-459 when layout == ISX_LAYOUT_NHWC.
+ *
+ * Geometry: input tiles B x C x H x W (or B x H x W x C), output B x C x outH x outW, always NCHW.
+ * outH == H and outW == W means "no resize"; otherwise every output pixel is the bilinear sample
+ * of the input, bit-identical to torch-CPU's upsample_bilinear2d, and is never materialised
+ * between the statistics pass and the apply pass.
+ */
+
+/* Bytes of scratch isx_preprocess_stats needs for C channels. */
+size_t isx_preprocess_stats_workspace_bytes(int C);
+
+/* Per-channel batch mean and unbiased std over (batch, height, width) of the (resized) tiles,
+ * transforms.py:62-65.  uint8 tiles without resize are reduced exactly in integers; every other
+ * case accumulates in fp64.  Results are rounded once to fp32: mean[C], std[C]. */
+int isx_preprocess_stats(const void* in, int in_dtype, int layout, int B, int C, int H, int W,
+                         int outH, int outW, float* mean, float* std, void* workspace,
+                         size_t workspace_bytes, isx_stream_t stream);
+
+/* out = clip((resize(x) - mean) / (std + eps), lo, hi), transforms.py:68-72, fp32 arithmetic with
+ * IEEE division (bit-identical to the reference given the same statistics).
+ * mean/std hold stat_batch x C floats, stat_batch in {1, B} ("#B C 1 1" broadcasting).
+ * out_dtype: ISX_DTYPE_F32 (reference behaviour) or ISX_DTYPE_BF16 (rounded from the fp32 value). */
+int isx_preprocess_apply(const void* in, int in_dtype, int layout, int B, int C, int H, int W,
+                         int outH, int outW, const float* mean, const float* std, int stat_batch,
+                         float eps, int has_lo, float lo, int has_hi, float hi, void* out,
+                         int out_dtype, isx_stream_t stream);
+
+/* resize only (transforms.py:78-126): out fp32 NCHW = bilinear(in). */
+int isx_resize_bilinear(const void* in, int in_dtype, int layout, int B, int C, int H, int W,
+                        int outH, int outW, float* out, isx_stream_t stream);
+
+/* ---- stage 2: L2-normalise (+ pool) + PCA projection ------------------------------------------
+ * Replaces models/embedding.py:74 `F.normalize(x, p=2, dim=1)`, data.py:112-118
+ * `get_flat_vectors`, models/decomposition.py:79-91 `PCA.forward` and the reshape/permute of
+ * models/pipelines.py:82-84, fused: the B x E x h x w feature map is read once.
+ */
+
+/* Bytes of the packed projection operand for F features and k components. */
+size_t isx_project_packed_bytes(int F, int k);
+
+/* Pack PCA weights once per fitted model: component_vectors element (f, j) is read at
+ * comps[f * ld_f + j * ld_k] (the reference stores a transposed view: ld_f = 1, ld_k = F),
+ * feature_means is F floats.  Writes bf16 hi/lo splits (K-major, k x F each) and the fp32 bias
+ * -(means . comps) into `packed`. */
+int isx_project_pack(const float* feature_means, const float* comps, int F, int k, int64_t ld_f,
+                     int64_t ld_k, void* packed, size_t packed_bytes, isx_stream_t stream);
+
+size_t isx_l2norm_project_workspace_bytes(int B, int E, int h, int w, int k, int pool);
+
+/* fmap: fp32 B x E x h x w (NCHW, contiguous).
+ * pool == 0: out is fp32 (B*h*w) x k row-major, i.e. B x k x h x w viewed with NHWC strides —
+ *            exactly the memory pipelines.py:82-84 returns.
+ * pool == 1: spatial mean of the normalised cells, then the projection: out is fp32 B x k.
+ * normalize == 0 skips the L2 step (plain PCA.transform of h*w == 1 rows: fmap is n x F). */
+int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, int normalize,
+                       const void* packed, int k, float* out, void* workspace,
+                       size_t workspace_bytes, isx_stream_t stream);
+
+/* ---- stage 3: exhaustive cosine k-NN -----------------------------------------------------------
+ * No reference counterpart; semantics are the composition of the reference's
+ * idioms: normalize(q) . normalize(e) with F.normalize's eps (embedding.py:74) and a stable
+ * (score descending, index ascending) top-k.
+ */
+
+/* rnorm[i] = 1 / max(||x_i||_2, eps) for the rows of a bf16 matrix n x d (fp32 accumulation). */
+int isx_row_rnorm_bf16(const void* x, int64_t n, int d, float eps, float* rnorm, isx_stream_t stream);
+
+size_t isx_knn_workspace_bytes(int64_t n, int q, int d, int k);
+
+/* store: bf16 n x d row-major; queries: bf16 q x d row-major; *_rnorm from isx_row_rnorm_bf16.
+ * out_scores fp32 q x k, out_idx int32 q x k = index_base + local row.  Rows are ordered by
+ * (score desc, index asc); if n < k the tail is (-inf, -1).  The q x n score matrix never exists
+ * in memory: top-k selection is fused into the GEMM epilogue. */
+int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const void* queries,
+                   const float* query_rnorm, int q, int d, int k, int64_t index_base,
+                   float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes,
+                   isx_stream_t stream);
+
+/* Merge g partial results (scores, idx: g x q x k, e.g. the NCCL all-gather of every shard's
+ * local top-k) into q x k with the same ordering.  idx < 0 marks padding. */
+int isx_topk_merge(const float* scores, const int32_t* idx, int g, int q, int k, float* out_scores,
+                   int32_t* out_idx, isx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMAGESCRY_B200_H_ */
