@@ -9,7 +9,7 @@ if [ ${#files[@]} -eq 0 ]; then files=(tests/test_gpu_preprocess.py tests/test_g
 rc_all=0
 for f in "${files[@]}"; do
   name=$(basename "$f" .py)
-  timeout 600 python -m pytest "$f" -q -m gpu -x --tb=short -p no:cacheprovider > "gpurun_out/${name}.log" 2>&1
+  timeout 600 python -m pytest "$f" -q -m gpu --tb=short -p no:cacheprovider > "gpurun_out/${name}.log" 2>&1
   rc=$?
   echo "$f -> exit $rc" | tee -a gpurun_out/diag_summary.txt
   tail -n 25 "gpurun_out/${name}.log"
