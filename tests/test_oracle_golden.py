@@ -203,3 +203,25 @@ def test_bf16_helpers():
     r = O.bf16_round(x)
     assert np.array_equal(O.bf16_from_bits(O.bf16_bits(x)), r)
     assert np.all(np.abs(r - x) <= np.abs(x) * 2.0**-8)
+
+
+# ------------------------------------------------------------------ torch-CPU port (timed baseline)
+def test_torch_port_matches_oracle(golden):
+    import torch
+
+    from oracle import torch_port as TP
+
+    torch.manual_seed(0)
+    g = golden("preprocess")
+    for msl in (640, 32):
+        out = TP.preprocess(torch.from_numpy(g["images"]), msl).numpy()
+        assert np.abs(out - g[f"pre_msl{msl}"]).max() <= 1e-6
+    ge = golden("embed_pca")
+    out = TP.l2_project(torch.from_numpy(ge["eb_fmap"]), torch.from_numpy(ge["eb_means"]), torch.from_numpy(ge["eb_comps"]))
+    assert np.allclose(out.numpy(), ge["eb_out_nchw"], rtol=1e-3, atol=1e-6)
+    rng = np.random.default_rng(0)
+    store = O.bf16_round(rng.standard_normal((5000, 64)).astype(np.float32))
+    q = O.bf16_round(rng.standard_normal((21, 64)).astype(np.float32))
+    s, i = TP.cosine_knn(torch.from_numpy(store), torch.from_numpy(q), 10, block=1024)
+    rs, ri = O.cosine_knn(store, q, 10)
+    assert np.array_equal(i.numpy(), ri) and np.allclose(s.numpy(), rs, atol=1e-5)
