@@ -127,13 +127,18 @@ struct KnnParams {
   float* part_scores;  // [splits][q][k]
   int32_t* part_idx;   // [splits][q][k]
   uint2* cand_global;  // [grid][BM][CAP] when k > kSmallK
+  uint32_t* thr_shared;  // [q] per-query lower bound on the global k-th best (ordered-uint encoding)
 };
 
+// Shared-memory plan.  k <= kSmallK: 32-entry per-row candidate buffers live in shared memory next to
+// a 4-stage operand ring (the buffers are XOR-swizzled by row so that 32 rows appending at the same
+// depth hit different banks).  Larger k: 256-entry buffers in the global workspace.
 template <int CAP>
 struct KnnSmem {
-  static constexpr int STAGES = (CAP <= 64) ? 3 : 4;
-  static constexpr uint32_t kCandStride = CAP + 1;  // (score, idx) pairs per row incl. padding
-  static constexpr uint32_t kCandBytes = (CAP <= 64) ? BM * kCandStride * 8 : 0;
+  static constexpr int STAGES = 4;
+  static constexpr bool kSmemCand = (CAP <= 32);
+  static constexpr int CHUNK = kSmemCand ? 16 : 32;  // accumulator columns per tcgen05.ld
+  static constexpr uint32_t kCandBytes = kSmemCand ? BM * CAP * 8 : 0;
   static constexpr uint32_t kAOff = 0;
   static constexpr uint32_t kBOff = kAOff + STAGES * A_STAGE_BYTES;
   static constexpr uint32_t kCandOff = kBOff + STAGES * B_STAGE_BYTES;
@@ -142,17 +147,35 @@ struct KnnSmem {
   static constexpr uint32_t kNumBars = 2 * STAGES + 2 * ACC_STAGES;
   static constexpr uint32_t kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr uint32_t kTotal = kTmemPtrOff + 16;
-  static constexpr uint32_t kDynamicBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
+  // the operand tiles need 1024-byte alignment; the dynamic window normally starts aligned, so only
+  // as much slack as the 227 KB limit leaves is requested and the kernel checks that it suffices
+  static constexpr uint32_t kMaxDynamic = 232448;
+  static constexpr uint32_t kDynamicBytes = (kTotal + 1024 <= kMaxDynamic) ? kTotal + 1024 : kMaxDynamic;
+  static_assert(kTotal <= kMaxDynamic, "shared-memory plan exceeds 227 KB");
 };
+
+// Monotonic float <-> uint32 map (0 = below everything) for atomicMax on thresholds.
+__device__ __forceinline__ uint32_t thr_encode(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+// Largest float strictly below the encoded value (so that `v > result` means `v >= value`).
+__device__ __forceinline__ float thr_decode_below(uint32_t u) {
+  if (u == 0) return -INFINITY;
+  const uint32_t w = u - 1;
+  const float f = __uint_as_float((w & 0x80000000u) ? (w & 0x7FFFFFFFu) : ~w);
+  return (f == 0.0f) ? __uint_as_float(0x80000001u) : f;
+}
 
 __device__ __forceinline__ void epilogue_bar_sync() {
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
 // Warp-cooperative prune of one row's candidate buffer: sort, keep the best k, return the new
-// threshold (score of the k-th best, or -inf while fewer than k candidates exist).
+// threshold (score of the k-th best, or -inf while fewer than k candidates exist).  Entry i of the
+// row lives at row_buf[i ^ swz] (swz = row % 32 for the shared-memory buffers, 0 in global memory).
 template <int CAP>
-__device__ __forceinline__ void prune_row(uint2* row_buf, int count, int k, float& new_thr,
+__device__ __forceinline__ void prune_row(uint2* row_buf, int swz, int count, int k, float& new_thr,
                                           int& new_count, float (&s)[CAP / 32], int (&idx)[CAP / 32]) {
   constexpr int E = CAP / 32;
   const int lane = static_cast<int>(lane_id());
@@ -160,7 +183,7 @@ __device__ __forceinline__ void prune_row(uint2* row_buf, int count, int k, floa
   for (int e = 0; e < E; ++e) {
     const int i = e * 32 + lane;
     if (i < count) {
-      const uint2 v = row_buf[i];
+      const uint2 v = row_buf[i ^ swz];
       s[e] = __uint_as_float(v.x);
       idx[e] = static_cast<int>(v.y);
     } else {
@@ -173,7 +196,7 @@ __device__ __forceinline__ void prune_row(uint2* row_buf, int count, int k, floa
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int i = e * 32 + lane;
-    if (i < k && i < count) row_buf[i] = make_uint2(__float_as_uint(s[e]), static_cast<uint32_t>(idx[e]));
+    if (i < k && i < count) row_buf[i ^ swz] = make_uint2(__float_as_uint(s[e]), static_cast<uint32_t>(idx[e]));
     const float cand = __shfl_sync(kFullMask, s[e], (k - 1) & 31);
     if (e == ((k - 1) >> 5)) kth = cand;
   }
@@ -190,6 +213,10 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   constexpr int E = CAP / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (threadIdx.x == 0 && static_cast<uint32_t>(smem - smem_raw) + L::kTotal > L::kDynamicBytes) {
+    printf("isx: knn_search_kernel: dynamic shared memory window is not 1024-byte aligned\n");
+    __trap();
+  }
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* full_bar = bars;
@@ -275,18 +302,20 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
   } else if (warp >= kEpilogueWarp0) {
     // ===================== epilogue: fused top-k =====================
+    constexpr int CHUNK = L::CHUNK;
     const int ew = warp - kEpilogueWarp0;     // == warp % 4: the TMEM lane quarter this warp may read
     const int row = ew * 32 + lane;           // query row inside the tile
     const int et = threadIdx.x - kEpilogueWarp0 * 32;  // 0..127
     uint2* cand_base;
     uint32_t cand_stride;
-    if (CAP <= 64) {
+    if (L::kSmemCand) {
       cand_base = reinterpret_cast<uint2*>(smem + L::kCandOff);
-      cand_stride = L::kCandStride;
+      cand_stride = CAP;
     } else {
       cand_base = p.cand_global + static_cast<size_t>(blockIdx.x) * BM * CAP;
       cand_stride = CAP;
     }
+    const int my_swz = L::kSmemCand ? lane : 0;
     uint2* my_buf = cand_base + static_cast<size_t>(row) * cand_stride;
     uint2* warp_buf = cand_base + static_cast<size_t>(ew * 32) * cand_stride;
 
@@ -299,6 +328,10 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const long long nb0 = p.nb * split / p.splits, nb1 = p.nb * (split + 1) / p.splits;
       const int qrow = mblk * BM + row;
       const bool row_valid = qrow < p.q;
+      // `thr`: a candidate must beat it.  It is the larger of this item's own k-th best and the
+      // bound every CTA working on the same query publishes in thr_shared: anything below the k-th
+      // best of ANY subset of the store cannot be in the global top-k, so other splits' progress
+      // prunes this one (the partial list may then hold fewer than k entries; the merge pads).
       float thr = row_valid ? -INFINITY : INFINITY;
       int cnt = 0;
 
@@ -310,20 +343,25 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         float* rn = rnorm_s + acc * BN;
         rn[et] = (et < ncols) ? __ldg(p.store_rnorm + n0 + et) : 0.f;
         rn[et + 128] = (et + 128 < ncols) ? __ldg(p.store_rnorm + n0 + et + 128) : 0.f;
+        if (row_valid) {
+          const uint32_t shared_u = *reinterpret_cast<const volatile uint32_t*>(p.thr_shared + qrow);
+          thr = fmaxf(thr, thr_decode_below(shared_u));
+        }
         epilogue_bar_sync();
 
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + chunk * 32, r);
+        for (int chunk = 0; chunk < BN / CHUNK; ++chunk) {
+          uint32_t r[CHUNK];
+          if (CHUNK == 32) tmem_ld_32x32(taddr + chunk * CHUNK, reinterpret_cast<uint32_t(&)[32]>(r));
+          else tmem_ld_32x16(taddr + chunk * CHUNK, reinterpret_cast<uint32_t(&)[16]>(r));
           tc_wait_ld();
-          const float4* rn4 = reinterpret_cast<const float4*>(rn + chunk * 32);
+          const float4* rn4 = reinterpret_cast<const float4*>(rn + chunk * CHUNK);
           float vmax = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < CHUNK / 4; ++j) {
             const float4 w = rn4[j];
             const float a = __uint_as_float(r[4 * j + 0]) * w.x;
             const float b = __uint_as_float(r[4 * j + 1]) * w.y;
@@ -336,19 +374,19 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             vmax = fmaxf(vmax, fmaxf(fmaxf(a, b), fmaxf(c, d)));
           }
           if (vmax > thr) {
-            // rare path: some score in this chunk beats the row's running k-th best
-            const int cbase = chunk * 32;
+            // rare path: some score in this chunk beats the row's threshold
+            const int cbase = chunk * CHUNK;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < CHUNK; ++j) {
               const float v = __uint_as_float(r[j]);
               if (v > thr && cbase + j < ncols) {
-                my_buf[cnt] = make_uint2(r[j], static_cast<uint32_t>(n0 + cbase + j));
+                my_buf[cnt ^ my_swz] = make_uint2(r[j], static_cast<uint32_t>(n0 + cbase + j));
                 ++cnt;
               }
             }
           }
           // warp-uniform: prune every row that could overflow during the next chunk
-          uint32_t need = __ballot_sync(kFullMask, cnt > CAP - 32);
+          uint32_t need = __ballot_sync(kFullMask, cnt > CAP - CHUNK);
           while (need) {
             const int rr = __ffs(need) - 1;
             need &= need - 1;
@@ -356,9 +394,16 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const int c = __shfl_sync(kFullMask, cnt, rr);
             float nthr;
             int ncnt;
-            prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, c, p.k, nthr, ncnt, s_reg, i_reg);
+            prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr,
+                           ncnt, s_reg, i_reg);
             __syncwarp();
-            if (lane == rr) { thr = nthr; cnt = ncnt; }
+            if (lane == rr) {
+              cnt = ncnt;
+              if (nthr > thr) {
+                thr = nthr;
+                atomicMax(p.thr_shared + qrow, thr_encode(nthr));
+              }
+            }
           }
         }
         // release the accumulator stage
@@ -377,8 +422,10 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const int qr = mblk * BM + ew * 32 + rr;
         float nthr;
         int ncnt;
-        prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, c, p.k, nthr, ncnt, s_reg, i_reg);
+        prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr, ncnt,
+                       s_reg, i_reg);
         if (qr < p.q) {
+          if (lane == 0 && nthr > -INFINITY) atomicMax(p.thr_shared + qr, thr_encode(nthr));
           float* os = p.part_scores + (static_cast<size_t>(split) * p.q + qr) * p.k;
           int32_t* oi = p.part_idx + (static_cast<size_t>(split) * p.q + qr) * p.k;
 #pragma unroll
@@ -470,7 +517,7 @@ int launch_merge(const float* scores, const int32_t* idx, int g, int q, int k, f
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct KnnWorkspace {
-  size_t part_scores_off, part_idx_off, cand_off, total;
+  size_t part_scores_off, part_idx_off, thr_off, cand_off, total;
 };
 
 KnnWorkspace knn_workspace(const KnnPlan& plan, int q, int k) {
@@ -480,6 +527,8 @@ KnnWorkspace knn_workspace(const KnnPlan& plan, int q, int k) {
   off = align_up(off + static_cast<size_t>(plan.splits) * q * k * sizeof(float), 256);
   w.part_idx_off = off;
   off = align_up(off + static_cast<size_t>(plan.splits) * q * k * sizeof(int32_t), 256);
+  w.thr_off = off;
+  off = align_up(off + static_cast<size_t>(q) * sizeof(uint32_t), 256);
   w.cand_off = off;
   if (k > kSmallK) off = align_up(off + static_cast<size_t>(plan.grid) * BM * 256 * sizeof(uint2), 256);
   w.total = off + 256;
@@ -573,8 +622,10 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
   p.part_scores = reinterpret_cast<float*>(wbase + ws.part_scores_off);
   p.part_idx = reinterpret_cast<int32_t*>(wbase + ws.part_idx_off);
   p.cand_global = reinterpret_cast<uint2*>(wbase + ws.cand_off);
+  p.thr_shared = reinterpret_cast<uint32_t*>(wbase + ws.thr_off);
+  ISX_CHECK_CUDA(cudaMemsetAsync(p.thr_shared, 0, static_cast<size_t>(q) * sizeof(uint32_t), stream));
 
-  if (k <= kSmallK) rc = launch_search<64>(tq, te, p, plan.grid, stream);
+  if (k <= kSmallK) rc = launch_search<32>(tq, te, p, plan.grid, stream);
   else rc = launch_search<256>(tq, te, p, plan.grid, stream);
   if (rc != ISX_OK) return rc;
   return launch_merge(p.part_scores, p.part_idx, plan.splits, q, k, out_scores, out_idx, stream);

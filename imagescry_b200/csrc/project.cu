@@ -117,6 +117,9 @@ __device__ __forceinline__ uint32_t bf16_hi_lo(float x, uint32_t& lo_bits) {
   return static_cast<uint32_t>(__bfloat16_as_ushort(hi));
 }
 
+// HW: cells per image known at compile time (256 = 16x16, 64 = 8x8 maps: channel strides become
+// immediate load offsets), or 0 for any shape.  The fast paths also need E % 64 == 0.
+template <int HW>
 __global__ void __launch_bounds__(kProjThreads, 1)
 l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_constant__ CUtensorMap tmap_wlo,
                       const ProjParams p) {
@@ -238,10 +241,22 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
       bool valid;
       const float* base = row_base(tile_iter, valid);
       const int f0 = kb * PK + half * 32;
+      if (HW > 0) {
+        // E % 64 == 0: every feature of the block exists; channel stride is a compile-time constant
+        const float* src = base + static_cast<long long>(f0) * HW;
+        if (valid) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int f = f0 + i;
-        x[i] = (valid && f < p.E) ? __ldg(base + static_cast<long long>(f) * p.hw) : 0.f;
+          for (int i = 0; i < 32; ++i) x[i] = __ldg(src + i * HW);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int f = f0 + i;
+          x[i] = (valid && f < p.E) ? __ldg(base + static_cast<long long>(f) * p.hw) : 0.f;
+        }
       }
     };
 
@@ -256,10 +271,14 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
         const float a = x[2 * i], b = x[2 * i + 1];
         ss = fmaf(a, a, ss);
         ss = fmaf(b, b, ss);
-        uint32_t la, lb;
-        const uint32_t ha = bf16_hi_lo(a, la), hb = bf16_hi_lo(b, lb);
-        hi[i] = ha | (hb << 16);
-        lo[i] = la | (lb << 16);
+        // hi = x truncated to bf16 (a mask, no conversion); lo = RN_bf16(x - hi), the subtraction is
+        // exact.  |x - hi - lo| <= 2^-16 |x|.
+        const uint32_t ab = __float_as_uint(a), bb = __float_as_uint(b);
+        hi[i] = __byte_perm(ab, bb, 0x7632);
+        const float la = a - __uint_as_float(ab & 0xFFFF0000u);
+        const float lb = b - __uint_as_float(bb & 0xFFFF0000u);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(la, lb);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
       }
       mbar_wait(&a_empty[stage], phase ^ 1);
       uint8_t* a_hi = smem + L::kAOff + stage * A_STAGE_BYTES_P + m * 128;
@@ -480,8 +499,11 @@ int launch_project(const float* fmap, long long m_total, int E, int hw, int k, i
   (void)fn;
   const int grid = static_cast<int>(std::min<long long>(sms, p.tiles));
   const int smem = static_cast<int>(ProjSmem::kDynamicBytes);
-  ISX_CHECK_CUDA(cudaFuncSetAttribute(l2norm_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  l2norm_project_kernel<<<grid, kProjThreads, smem, stream>>>(twh, twl, p);
+  auto kern = l2norm_project_kernel<0>;
+  if (E % PK == 0 && hw == 256) kern = l2norm_project_kernel<256>;
+  else if (E % PK == 0 && hw == 64) kern = l2norm_project_kernel<64>;
+  ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, kProjThreads, smem, stream>>>(twh, twl, p);
   ISX_CHECK_CUDA(cudaGetLastError());
   return ISX_OK;
 }
