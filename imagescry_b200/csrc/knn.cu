@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 
 namespace isx {
 namespace {
@@ -42,8 +43,7 @@ constexpr int kEpilogueWarp0 = 4;
 constexpr int kMaxK = 128;
 constexpr int kSmallK = 16;  // k <= kSmallK keeps candidate buffers in shared memory
 
-constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KB per CTA
 
 struct KnnPlan {
   int mb;        // 128-query blocks
@@ -53,9 +53,11 @@ struct KnnPlan {
   int grid;
 };
 
-KnnPlan plan_knn(long long n, int q, int sms) {
+// ncta = 2: CTA pairs (cta_group::2) — an M block is 256 queries and the schedulable units are SM pairs.
+KnnPlan plan_knn(long long n, int q, int sms_total, int ncta) {
   KnnPlan p;
-  p.mb = (q + BM - 1) / BM;
+  const int sms = std::max(1, sms_total / ncta);
+  p.mb = (q + BM * ncta - 1) / (BM * ncta);
   p.nb = (n + BN - 1) / BN;
   if (p.nb < 1) p.nb = 1;
   const long long max_s = std::max<long long>(1, std::min<long long>(p.nb, 4096));
@@ -74,7 +76,7 @@ KnnPlan plan_knn(long long n, int q, int sms) {
   }
   p.splits = best_s;
   p.items = static_cast<long long>(p.mb) * p.splits;
-  p.grid = static_cast<int>(std::min<long long>(sms, p.items));
+  p.grid = static_cast<int>(std::min<long long>(sms, p.items)) * ncta;
   return p;
 }
 
@@ -133,9 +135,10 @@ struct KnnParams {
 // Shared-memory plan.  k <= kSmallK: 32-entry per-row candidate buffers live in shared memory next to
 // a 4-stage operand ring (the buffers are XOR-swizzled by row so that 32 rows appending at the same
 // depth hit different banks).  Larger k: 256-entry buffers in the global workspace.
-template <int CAP>
+template <int CAP, int NCTA>
 struct KnnSmem {
-  static constexpr int STAGES = 4;
+  static constexpr uint32_t B_STAGE_BYTES = (BN / NCTA) * BK * 2;  // 32 KB, or 16 KB per CTA of a pair
+  static constexpr int STAGES = (NCTA == 2) ? 6 : 4;
   static constexpr bool kSmemCand = (CAP <= 32);
   static constexpr int CHUNK = kSmemCand ? 16 : 32;  // accumulator columns per tcgen05.ld
   static constexpr uint32_t kCandBytes = kSmemCand ? BM * CAP * 8 : 0;
@@ -204,12 +207,18 @@ __device__ __forceinline__ void prune_row(uint2* row_buf, int swz, int count, in
   new_thr = (count >= k) ? kth : -INFINITY;
 }
 
-template <int CAP>
+template <int CAP, int NCTA>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
                   const KnnParams p) {
-  using L = KnnSmem<CAP>;
+  using L = KnnSmem<CAP, NCTA>;
   constexpr int STAGES = L::STAGES;
+  constexpr uint32_t B_STAGE_BYTES = L::B_STAGE_BYTES;
+  // NCTA == 2: this CTA and its cluster peer form one MMA of M = 256 (cta_group::2).  Rank r owns
+  // query rows [128 r, 128 r + 128) of the 256-row block and loads store rows [128 r, 128 r + 128) of
+  // every 256-row store tile; the leader (rank 0) issues the MMAs for both.
+  const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  const long long unit = blockIdx.x / NCTA, num_units = gridDim.x / NCTA;
   constexpr int E = CAP / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -235,16 +244,16 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     prefetch_tmap(&tmap_e);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], NCTA); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * NCTA); }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
+    if (NCTA == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -252,18 +261,27 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+      for (long long item = unit; item < p.items; item += num_units) {
         const int split = static_cast<int>(item / p.mb);
         const int mblk = static_cast<int>(item - static_cast<long long>(split) * p.mb);
         const long long nb0 = p.nb * split / p.splits, nb1 = p.nb * (split + 1) / p.splits;
+        const int32_t m0 = (mblk * NCTA + static_cast<int>(rank)) * BM;
         for (long long nb = nb0; nb < nb1; ++nb) {
+          const int32_t n0 = static_cast<int32_t>(nb * BN) + static_cast<int32_t>(rank) * (BN / NCTA);
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-            tma_load_2d(smem + L::kAOff + stage * A_STAGE_BYTES, &tmap_q, &full_bar[stage], kb * BK,
-                        mblk * BM, kEvictLast);
-            tma_load_2d(smem + L::kBOff + stage * B_STAGE_BYTES, &tmap_e, &full_bar[stage], kb * BK,
-                        static_cast<int32_t>(nb * BN), kEvictNormal);
+            uint8_t* a_dst = smem + L::kAOff + stage * A_STAGE_BYTES;
+            uint8_t* b_dst = smem + L::kBOff + stage * B_STAGE_BYTES;
+            if (NCTA == 2) {
+              // both CTAs report to the leader's barrier (count 2, 2 x 32 KB of transactions)
+              mbar_arrive_expect_tx_leader(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+              tma_load_2d_pair(a_dst, &tmap_q, &full_bar[stage], kb * BK, m0, kEvictLast);
+              tma_load_2d_pair(b_dst, &tmap_e, &full_bar[stage], kb * BK, n0, kEvictNormal);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+              tma_load_2d(a_dst, &tmap_q, &full_bar[stage], kb * BK, m0, kEvictLast);
+              tma_load_2d(b_dst, &tmap_e, &full_bar[stage], kb * BK, n0, kEvictNormal);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -271,10 +289,10 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, BM * NCTA, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+      for (long long item = unit; item < p.items; item += num_units) {
         const int split = static_cast<int>(item / p.mb);
         const long long nb0 = p.nb * split / p.splits, nb1 = p.nb * (split + 1) / p.splits;
         for (long long nb = nb0; nb < nb1; ++nb) {
@@ -290,12 +308,15 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t a_desc = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 2);
               const uint64_t b_desc = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2);
-              tc_mma_f16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+              if (NCTA == 2) tc_mma_f16_pair(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+              else tc_mma_f16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
             }
-            tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+            if (NCTA == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&tmem_full[acc]);  // accumulator complete
+          // accumulator complete
+          if (NCTA == 2) tc_commit_pair(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -322,11 +343,12 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint32_t acc = 0, acc_phase = 0;
     float s_reg[E];
     int i_reg[E];
-    for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+    for (long long item = unit; item < p.items; item += num_units) {
       const int split = static_cast<int>(item / p.mb);
       const int mblk = static_cast<int>(item - static_cast<long long>(split) * p.mb);
       const long long nb0 = p.nb * split / p.splits, nb1 = p.nb * (split + 1) / p.splits;
-      const int qrow = mblk * BM + row;
+      const int m0 = (mblk * NCTA + static_cast<int>(rank)) * BM;
+      const int qrow = m0 + row;
       const bool row_valid = qrow < p.q;
       // `thr`: a candidate must beat it.  It is the larger of this item's own k-th best and the
       // bound every CTA working on the same query publishes in thr_shared: anything below the k-th
@@ -409,7 +431,9 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // release the accumulator stage
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
+        }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
 
@@ -419,7 +443,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         __syncwarp();
         const int c = __shfl_sync(kFullMask, cnt, rr);
         const float rq = __shfl_sync(kFullMask, rq_mine, rr);
-        const int qr = mblk * BM + ew * 32 + rr;
+        const int qr = m0 + ew * 32 + rr;
         float nthr;
         int ncnt;
         prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr, ncnt,
@@ -444,10 +468,10 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();  // a pair's CTAs may not exit while the peer uses them
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (NCTA == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -535,14 +559,37 @@ KnnWorkspace knn_workspace(const KnnPlan& plan, int q, int k) {
   return w;
 }
 
-template <int CAP>
+template <int CAP, int NCTA>
 int launch_search(const CUtensorMap& tq, const CUtensorMap& te, const KnnParams& p, int grid, cudaStream_t stream) {
-  auto kern = knn_search_kernel<CAP>;
-  const int smem = static_cast<int>(KnnSmem<CAP>::kDynamicBytes);
+  auto kern = knn_search_kernel<CAP, NCTA>;
+  const int smem = static_cast<int>(KnnSmem<CAP, NCTA>::kDynamicBytes);
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, kKnnThreads, smem, stream>>>(tq, te, p);
-  ISX_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kKnnThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ISX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, te, p));
   return ISX_OK;
+}
+
+// CTA pairs halve the shared-memory fill and operand-read traffic per SM (each CTA stages half of
+// every store tile).  They need at least two 128-query blocks to pay off; ISX_KNN_CTA_PAIR=0/1
+// overrides the choice (for A/B measurements).
+int knn_ncta(int q) {
+  static const int forced = [] {
+    const char* e = getenv("ISX_KNN_CTA_PAIR");
+    return (e && (e[0] == '0' || e[0] == '1')) ? (e[0] - '0') : -1;
+  }();
+  if (forced >= 0) return forced ? 2 : 1;
+  return q > BM ? 2 : 1;
 }
 
 }  // namespace
@@ -573,8 +620,8 @@ size_t isx_knn_workspace_bytes(int64_t n, int q, int d, int k) {
   if (n <= 0 || q <= 0 || k <= 0 || k > kMaxK) return 0;
   int sms = 148;
   if (device_sm_count(&sms) != ISX_OK) sms = 148;
-  const KnnPlan plan = plan_knn(n, q, sms);
-  return knn_workspace(plan, q, k).total;
+  // cover either scheduling mode (the choice may be overridden at search time)
+  return std::max(knn_workspace(plan_knn(n, q, sms, 1), q, k).total, knn_workspace(plan_knn(n, q, sms, 2), q, k).total);
 }
 
 int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const void* queries,
@@ -599,7 +646,8 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
   int sms = 148;
   int rc = device_sm_count(&sms);
   if (rc != ISX_OK) return rc;
-  const KnnPlan plan = plan_knn(n, q, sms);
+  const int ncta = (sms >= 2) ? knn_ncta(q) : 1;
+  const KnnPlan plan = plan_knn(n, q, sms, ncta);
   const KnnWorkspace ws = knn_workspace(plan, q, k);
   ISX_REQUIRE(workspace != nullptr && workspace_bytes >= ws.total, "%s: workspace too small (%zu < %zu)", fn,
               workspace_bytes, ws.total);
@@ -610,7 +658,7 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
                       static_cast<uint64_t>(d), static_cast<uint64_t>(d) * 2, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != ISX_OK) return rc;
   rc = encode_tmap_2d(&te, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, store, static_cast<uint64_t>(n),
-                      static_cast<uint64_t>(d), static_cast<uint64_t>(d) * 2, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+                      static_cast<uint64_t>(d), static_cast<uint64_t>(d) * 2, BN / ncta, BK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != ISX_OK) return rc;
 
   KnnParams p;
@@ -625,8 +673,13 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
   p.thr_shared = reinterpret_cast<uint32_t*>(wbase + ws.thr_off);
   ISX_CHECK_CUDA(cudaMemsetAsync(p.thr_shared, 0, static_cast<size_t>(q) * sizeof(uint32_t), stream));
 
-  if (k <= kSmallK) rc = launch_search<32>(tq, te, p, plan.grid, stream);
-  else rc = launch_search<256>(tq, te, p, plan.grid, stream);
+  if (ncta == 2) {
+    if (k <= kSmallK) rc = launch_search<32, 2>(tq, te, p, plan.grid, stream);
+    else rc = launch_search<256, 2>(tq, te, p, plan.grid, stream);
+  } else {
+    if (k <= kSmallK) rc = launch_search<32, 1>(tq, te, p, plan.grid, stream);
+    else rc = launch_search<256, 1>(tq, te, p, plan.grid, stream);
+  }
   if (rc != ISX_OK) return rc;
   return launch_merge(p.part_scores, p.part_idx, plan.splits, q, k, out_scores, out_idx, stream);
 }

@@ -69,6 +69,9 @@ def check(store, queries, k, scores, idx, index_base=0):
         (3000, 50, 1280, 100),   # k = 100 path (global candidate buffers)
         (700, 33, 72, 100),      # d not a multiple of 64
         (40000, 300, 128, 10),   # several N-splits
+        (2000, 257, 128, 10),    # CTA pairs: the second pair holds one query row
+        (2500, 513, 64, 100),    # CTA pairs with global candidate buffers, ragged store tile
+        (60000, 1000, 256, 32),  # pairs x splits x k between the two candidate-buffer regimes
     ],
 )
 def test_knn_vs_oracle(n, q, d, k):
