@@ -119,6 +119,30 @@ def test_preprocess_vs_oracle_u8(case, layout):
     del rm, rs
 
 
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_resize_normalize_division_bit_exact_many_divisors(layout):
+    """The three-channel resize kernel hoists the reciprocal of div.rn.f32's fast path out of the
+    pixel loop; (x - m) / (s + eps) must still be the IEEE quotient for every divisor.  96 images,
+    each with its own per-image statistics over ten decades, plus divisors outside the hoisted
+    path's range (they take the per-pixel IEEE division)."""
+    rng = np.random.default_rng(2024)
+    B, H, W, oh, ow = 96, 40, 56, 23, 31
+    x = rng.integers(0, 256, (B, 3, H, W), dtype=np.uint8)
+    xin = x if layout == "nchw" else np.ascontiguousarray(x.transpose(0, 2, 3, 1))
+    lay = O.NCHW if layout == "nchw" else O.NHWC
+    res = O.bilinear_resize(xin, oh, ow, layout=lay)
+    pm = rng.uniform(-300, 300, (B, 3, 1, 1)).astype(np.float32)
+    ps = (10.0 ** rng.uniform(-5, 5, (B, 3, 1, 1))).astype(np.float32)
+    ps[0] = 1e-30   # outside [2^-60, 2^60]: per-pixel IEEE division
+    ps[1] = 3e25
+    pm[2] = 5e7     # |mean| beyond the hoisted path's bound
+    pm[3] = 0.0     # x - m can be exactly 0 and tiny
+    for kw in (dict(), dict(min_value=-3, max_value=3), dict(min_value=-0.5)):
+        ref = O.normalize_per_channel(res, channel_means=pm, channel_stds=ps, **kw)
+        out = T.preprocess_tiles(dev(xin), layout=layout, output_hw=(oh, ow), channel_means=dev(pm), channel_stds=dev(ps), **kw)
+        assert np.array_equal(host(out), ref), kw
+
+
 def test_preprocess_float_input_and_stats_ulps():
     rng = np.random.default_rng(7)
     x = rng.standard_normal((4, 3, 33, 47)).astype(np.float32) * 50 + 120
