@@ -28,6 +28,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace isx {
 namespace {
@@ -42,11 +43,17 @@ constexpr int kMaxComponents = 256;
 
 constexpr uint32_t A_PART_BYTES = PM * PK * 2;           // 16 KB (one of hi / lo)
 constexpr uint32_t A_STAGE_BYTES_P = 2 * A_PART_BYTES;   // hi + lo
-constexpr uint32_t W_PART_BYTES = kMaxComponents * PK * 2;  // 32 KB
-constexpr uint32_t W_STAGE_BYTES = 2 * W_PART_BYTES;
-constexpr int A_STAGES = 2, W_STAGES = 2, P_ACC_STAGES = 2;
+constexpr int P_ACC_STAGES = 2;
 
+// NCTA == 2 (CTA pair, cta_group::2): each CTA transforms its own 128 cells but stages only half of
+// the weight rows of every k-block, so the L2 -> shared-memory weight stream per SM halves and the
+// freed shared memory buys a third stage for both rings.
+template <int NCTA>
 struct ProjSmem {
+  static constexpr uint32_t W_PART_BYTES = (kMaxComponents / NCTA) * PK * 2;  // 32 KB, or 16 KB per CTA of a pair
+  static constexpr uint32_t W_STAGE_BYTES = 2 * W_PART_BYTES;                 // hi + lo
+  static constexpr int A_STAGES = (NCTA == 2) ? 3 : 2;
+  static constexpr int W_STAGES = (NCTA == 2) ? 3 : 2;
   static constexpr uint32_t kAOff = 0;
   static constexpr uint32_t kWOff = kAOff + A_STAGES * A_STAGE_BYTES_P;      // 64 KB
   static constexpr uint32_t kSsOff = kWOff + W_STAGES * W_STAGE_BYTES;       // +128 KB
@@ -110,24 +117,21 @@ struct ProjParams {
   float* out;
 };
 
-__device__ __forceinline__ uint32_t bf16_hi_lo(float x, uint32_t& lo_bits) {
-  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-  lo_bits = static_cast<uint32_t>(__bfloat16_as_ushort(lo));
-  return static_cast<uint32_t>(__bfloat16_as_ushort(hi));
-}
-
 // HW: cells per image known at compile time (256 = 16x16, 64 = 8x8 maps: channel strides become
 // immediate load offsets), or 0 for any shape.  The fast paths also need E % 64 == 0.
-template <int HW>
+template <int HW, int NCTA>
 __global__ void __launch_bounds__(kProjThreads, 1)
 l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_constant__ CUtensorMap tmap_wlo,
                       const ProjParams p) {
-  using L = ProjSmem;
+  using L = ProjSmem<NCTA>;
+  constexpr int A_STAGES = L::A_STAGES, W_STAGES = L::W_STAGES;
+  constexpr uint32_t W_PART_BYTES = L::W_PART_BYTES, W_STAGE_BYTES = L::W_STAGE_BYTES;
+  const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  const long long unit = blockIdx.x / NCTA, num_units = gridDim.x / NCTA;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* a_full = bars;                        // [A_STAGES]  count 256 (transform threads)
+  uint64_t* a_full = bars;                        // [A_STAGES]  8 transform warps per CTA (on the leader)
   uint64_t* a_empty = a_full + A_STAGES;          // [A_STAGES]  tcgen05.commit
   uint64_t* w_full = a_empty + A_STAGES;          // [W_STAGES]  TMA
   uint64_t* w_empty = w_full + W_STAGES;          // [W_STAGES]  tcgen05.commit
@@ -148,48 +152,56 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
     prefetch_tmap(&tmap_wlo);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], kTransformThreads); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], (kTransformThreads / 32) * NCTA); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&w_full[i], NCTA); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < P_ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 4 * NCTA);
       mbar_init(&ss_full[i], kTransformThreads);
       mbar_init(&ss_empty[i], 4);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
+    if (NCTA == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
   }
   for (int i = threadIdx.x; i < kMaxComponents; i += blockDim.x) bias_s[i] = (i < p.k_pad) ? p.bias[i] : 0.f;
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t w_part_bytes = static_cast<uint32_t>(p.k_pad) * PK * 2;
+  const int w_rows = p.k_pad / NCTA;  // weight rows (components) this CTA stages per k-block
+  const uint32_t w_part_bytes = static_cast<uint32_t>(w_rows) * PK * 2;
 
   if (warp == 0) {
     // ===================== weight TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      const int32_t row0 = static_cast<int32_t>(rank) * w_rows;
+      for (long long tile = unit; tile < p.tiles; tile += num_units) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&w_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&w_full[stage], 2 * w_part_bytes);
           uint8_t* dst = smem + L::kWOff + stage * W_STAGE_BYTES;
-          tma_load_2d(dst, &tmap_whi, &w_full[stage], kb * PK, 0, kEvictLast);
-          tma_load_2d(dst + W_PART_BYTES, &tmap_wlo, &w_full[stage], kb * PK, 0, kEvictLast);
+          if (NCTA == 2) {
+            mbar_arrive_expect_tx_leader(&w_full[stage], 2 * w_part_bytes);
+            tma_load_2d_pair(dst, &tmap_whi, &w_full[stage], kb * PK, row0, kEvictLast);
+            tma_load_2d_pair(dst + W_PART_BYTES, &tmap_wlo, &w_full[stage], kb * PK, row0, kEvictLast);
+          } else {
+            mbar_arrive_expect_tx(&w_full[stage], 2 * w_part_bytes);
+            tma_load_2d(dst, &tmap_whi, &w_full[stage], kb * PK, 0, kEvictLast);
+            tma_load_2d(dst + W_PART_BYTES, &tmap_wlo, &w_full[stage], kb * PK, 0, kEvictLast);
+          }
           if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(/*bf16*/ 1, PM, static_cast<uint32_t>(p.k_pad));
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(/*bf16*/ 1, PM * NCTA, static_cast<uint32_t>(p.k_pad));
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, acc = 0, acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      for (long long tile = unit; tile < p.tiles; tile += num_units) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kMaxComponents;
@@ -206,16 +218,22 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
             const uint32_t o = k * P_UMMA_K * 2;
             const uint64_t dah = make_kmajor_sw128_desc(a_hi + o), dal = make_kmajor_sw128_desc(a_lo + o);
             const uint64_t dwh = make_kmajor_sw128_desc(w_hi + o), dwl = make_kmajor_sw128_desc(w_lo + o);
-            tc_mma_f16(d_tmem, dah, dwh, idesc, (kb | k) != 0);
-            tc_mma_f16(d_tmem, dal, dwh, idesc, 1);
-            tc_mma_f16(d_tmem, dah, dwl, idesc, 1);
+            if (NCTA == 2) {
+              tc_mma_f16_pair(d_tmem, dah, dwh, idesc, (kb | k) != 0);
+              tc_mma_f16_pair(d_tmem, dal, dwh, idesc, 1);
+              tc_mma_f16_pair(d_tmem, dah, dwl, idesc, 1);
+            } else {
+              tc_mma_f16(d_tmem, dah, dwh, idesc, (kb | k) != 0);
+              tc_mma_f16(d_tmem, dal, dwh, idesc, 1);
+              tc_mma_f16(d_tmem, dah, dwl, idesc, 1);
+            }
           }
-          tc_commit(&a_empty[as]);
-          tc_commit(&w_empty[ws]);
+          if (NCTA == 2) { tc_commit_pair(&a_empty[as]); tc_commit_pair(&w_empty[ws]); }
+          else { tc_commit(&a_empty[as]); tc_commit(&w_empty[ws]); }
           if (++as == A_STAGES) { as = 0; aph ^= 1; }
           if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);
+        if (NCTA == 2) tc_commit_pair(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);
         if (++acc == P_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -224,12 +242,12 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
     const int t = threadIdx.x - kTransformWarp0 * 32;  // 0..255
     const int m = t & (PM - 1);                        // row (cell) inside the tile
     const int half = t >> 7;                           // which 32 of the k-block's 64 features
-    const long long my_tiles = (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const long long my_tiles = (p.tiles - unit + num_units - 1) / num_units;
     const long long total_seq = my_tiles * num_kb;
 
     auto row_base = [&](long long tile_iter, bool& valid) -> const float* {
-      const long long tile = blockIdx.x + tile_iter * gridDim.x;
-      const long long R = tile * PM + m;
+      const long long tile = unit + tile_iter * num_units;
+      const long long R = (tile * NCTA + rank) * PM + m;
       valid = R < p.m_total;
       const long long img = valid ? R / p.hw : 0;
       const long long cell = valid ? R - img * p.hw : 0;
@@ -263,8 +281,8 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
     float ss = 0.f;
     uint32_t acc = 0, acc_phase = 0;
     auto process = [&](float (&x)[32], long long seq) {
-      const uint32_t stage = static_cast<uint32_t>(seq & 1);
-      const uint32_t phase = static_cast<uint32_t>((seq >> 1) & 1);
+      const uint32_t stage = static_cast<uint32_t>(seq % A_STAGES);
+      const uint32_t phase = static_cast<uint32_t>((seq / A_STAGES) & 1);
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -290,7 +308,10 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
         *reinterpret_cast<uint4*>(a_lo + chunk * 16) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
-      mbar_arrive(&a_full[stage]);
+      __syncwarp();
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_leader(&a_full[stage]); else mbar_arrive(&a_full[stage]);
+      }
       const long long tile_iter = seq / num_kb;
       if (seq - tile_iter * num_kb == num_kb - 1) {
         // last k-block of the tile: publish this thread's share of the row's sum of squares
@@ -318,8 +339,8 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
     const int row = ew * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
     const bool vec_ok = (p.k & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0;
-    for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-      const long long R = tile * PM + row;
+    for (long long tile = unit; tile < p.tiles; tile += num_units) {
+      const long long R = (tile * NCTA + rank) * PM + row;
       mbar_wait(&ss_full[acc], acc_phase);
       float rn = 1.0f;
       if (p.normalize) {
@@ -354,16 +375,18 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == P_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (NCTA == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -474,18 +497,49 @@ l2norm_pool_kernel(const float* __restrict__ fmap, int B, int E, int hw, float* 
   }
 }
 
-int launch_project(const float* fmap, long long m_total, int E, int hw, int k, int normalize,
-                   const void* packed, float* out, cudaStream_t stream, const char* fn) {
+int project_ncta() {
+  static const int forced = [] {
+    const char* e = getenv("ISX_PROJECT_CTA_PAIR");
+    return (e && (e[0] == '0' || e[0] == '1')) ? (e[0] - '0') : -1;
+  }();
+  return forced == 0 ? 1 : 2;
+}
+
+template <int HW, int NCTA>
+int launch_project_kernel(const CUtensorMap& twh, const CUtensorMap& twl, const ProjParams& p, int grid,
+                          cudaStream_t stream) {
+  auto kern = l2norm_project_kernel<HW, NCTA>;
+  const int smem = static_cast<int>(ProjSmem<NCTA>::kDynamicBytes);
+  ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kProjThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ISX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, twh, twl, p));
+  return ISX_OK;
+}
+
+template <int NCTA>
+int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k, int normalize,
+                     const void* packed, float* out, cudaStream_t stream) {
   const PackedLayout l = packed_layout(E, k);
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
   CUtensorMap twh, twl;
   int rc = encode_tmap_2d(&twh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pk + l.hi_off, static_cast<uint64_t>(l.k_pad),
                           static_cast<uint64_t>(l.f_pad), static_cast<uint64_t>(l.f_pad) * 2,
-                          static_cast<uint32_t>(l.k_pad), PK, CU_TENSOR_MAP_SWIZZLE_128B);
+                          static_cast<uint32_t>(l.k_pad / NCTA), PK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != ISX_OK) return rc;
   rc = encode_tmap_2d(&twl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pk + l.lo_off, static_cast<uint64_t>(l.k_pad),
                       static_cast<uint64_t>(l.f_pad), static_cast<uint64_t>(l.f_pad) * 2,
-                      static_cast<uint32_t>(l.k_pad), PK, CU_TENSOR_MAP_SWIZZLE_128B);
+                      static_cast<uint32_t>(l.k_pad / NCTA), PK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != ISX_OK) return rc;
   int sms = 148;
   rc = device_sm_count(&sms);
@@ -493,19 +547,23 @@ int launch_project(const float* fmap, long long m_total, int E, int hw, int k, i
   ProjParams p;
   p.fmap = fmap; p.m_total = m_total; p.E = E; p.hw = hw; p.k = k; p.k_pad = l.k_pad;
   p.normalize = normalize;
-  p.tiles = (m_total + PM - 1) / PM;
+  p.tiles = (m_total + PM * NCTA - 1) / (PM * NCTA);  // tiles of 128 cells per CTA (256 per pair)
   p.bias = reinterpret_cast<const float*>(pk + l.bias_off);
   p.out = out;
+  const int grid = static_cast<int>(std::min<long long>(sms / NCTA, p.tiles)) * NCTA;
+  if (E % PK == 0 && hw == 256) return launch_project_kernel<256, NCTA>(twh, twl, p, grid, stream);
+  if (E % PK == 0 && hw == 64) return launch_project_kernel<64, NCTA>(twh, twl, p, grid, stream);
+  return launch_project_kernel<0, NCTA>(twh, twl, p, grid, stream);
+}
+
+int launch_project(const float* fmap, long long m_total, int E, int hw, int k, int normalize,
+                   const void* packed, float* out, cudaStream_t stream, const char* fn) {
   (void)fn;
-  const int grid = static_cast<int>(std::min<long long>(sms, p.tiles));
-  const int smem = static_cast<int>(ProjSmem::kDynamicBytes);
-  auto kern = l2norm_project_kernel<0>;
-  if (E % PK == 0 && hw == 256) kern = l2norm_project_kernel<256>;
-  else if (E % PK == 0 && hw == 64) kern = l2norm_project_kernel<64>;
-  ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, kProjThreads, smem, stream>>>(twh, twl, p);
-  ISX_CHECK_CUDA(cudaGetLastError());
-  return ISX_OK;
+  int sms = 148;
+  int rc = device_sm_count(&sms);
+  if (rc != ISX_OK) return rc;
+  if (sms >= 2 && project_ncta() == 2) return launch_project_n<2>(fmap, m_total, E, hw, k, normalize, packed, out, stream);
+  return launch_project_n<1>(fmap, m_total, E, hw, k, normalize, packed, out, stream);
 }
 
 }  // namespace
