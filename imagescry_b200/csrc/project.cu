@@ -497,6 +497,114 @@ l2norm_pool_kernel(const float* __restrict__ fmap, int B, int E, int hw, float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K3p (TMA flavour): the same single pass, but every 16-cell slab [E][16] arrives by TMA
+// (3-D tensor map over (cell, feature, image), boxes of 16 cells x 256 features) into one of two
+// 80 KB buffers while the CTA works on the other: memory latency is hidden by up to 80 KB in flight
+// per SM instead of per-thread cp.async granules.  Needs hw % 4 == 0 (16-byte global strides).
+// ------------------------------------------------------------------------------------------
+constexpr int kPoolFeatBox = 256;  // features per TMA box
+
+__global__ void __launch_bounds__(kPoolThreads, 1)
+l2norm_pool_tma_kernel(const __grid_constant__ CUtensorMap tmap, int B, int E, int hw, float* __restrict__ pooled) {
+  extern __shared__ uint8_t pool_tma_raw[];
+  // TMA destinations need 128-byte alignment; the dynamic window follows the static arrays below
+  uint8_t* pool_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pool_tma_raw) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ float part[16][kSlabCells];
+  __shared__ __align__(16) float rn_s[kSlabCells];
+  const int t = threadIdx.x;
+  const int nbox = (E + kPoolFeatBox - 1) / kPoolFeatBox;
+  const uint32_t slab_bytes = static_cast<uint32_t>(nbox) * kPoolFeatBox * kSlabCells * 4;
+  const int nslab = (hw + kSlabCells - 1) / kSlabCells;
+  const long long my_images = (B - static_cast<long long>(blockIdx.x) + gridDim.x - 1) / gridDim.x;
+  const long long total = my_images * nslab;
+
+  if (t == 0) {
+    prefetch_tmap(&tmap);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](long long seq) {  // thread 0 only
+    const int buf = static_cast<int>(seq & 1);
+    const long long img = blockIdx.x + (seq / nslab) * gridDim.x;
+    const int slab = static_cast<int>(seq % nslab);
+    mbar_arrive_expect_tx(&full_bar[buf], slab_bytes);
+    uint8_t* dst = pool_smem + static_cast<size_t>(buf) * slab_bytes;
+    for (int bx = 0; bx < nbox; ++bx)
+      tma_load_3d(dst + static_cast<size_t>(bx) * kPoolFeatBox * kSlabCells * 4, &tmap, &full_bar[buf],
+                  slab * kSlabCells, bx * kPoolFeatBox, static_cast<int32_t>(img), kEvictFirst);
+  };
+
+  float acc[kPoolMaxAcc / 4];  // features t + 256 j
+#pragma unroll
+  for (int j = 0; j < kPoolMaxAcc / 4; ++j) acc[j] = 0.f;
+  if (t == 0 && total > 0) issue(0);
+  for (long long seq = 0; seq < total; ++seq) {
+    const int buf = static_cast<int>(seq & 1);
+    // the other buffer was released by the barrier that ended iteration seq - 1
+    if (t == 0 && seq + 1 < total) issue(seq + 1);
+    mbar_wait(&full_bar[buf], static_cast<uint32_t>((seq >> 1) & 1));
+    const float* cur = reinterpret_cast<const float*>(pool_smem + static_cast<size_t>(buf) * slab_bytes);
+    const int slab = static_cast<int>(seq % nslab);
+    // per-cell sum of squares: thread = (cell, part); a warp reads two whole 64-byte rows per step
+    {
+      const int cell = t & 15, prt = t >> 4;
+      float ssq = 0.f;
+      for (int e = prt; e < E; e += 16) {
+        const float v = cur[e * kSlabCells + cell];
+        ssq = fmaf(v, v, ssq);
+      }
+      part[prt][cell] = ssq;
+    }
+    __syncthreads();
+    if (t < kSlabCells) {
+      float ssq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) ssq += part[i][t];
+      const bool live = slab * kSlabCells + t < hw;
+      rn_s[t] = live ? 1.0f / fmaxf(sqrtf(ssq), 1e-12f) : 0.f;
+    }
+    __syncthreads();
+    // weighted channel sums: thread owns features t + 256 j and reads their whole 16-cell rows; the
+    // quad order is rotated by row so that eight lanes cover all 32 banks
+    {
+      const int rot = (t >> 1) & 3;
+      float4 w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(&rn_s[((i + rot) & 3) * 4]);
+#pragma unroll
+      for (int j = 0; j < kPoolMaxAcc / 4; ++j) {
+        const int e = t + kPoolThreads * j;
+        if (e < E) {
+          const float* row = cur + e * kSlabCells;
+          float a = acc[j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(row + ((i + rot) & 3) * 4);
+            a = fmaf(v.x, w[i].x, fmaf(v.y, w[i].y, fmaf(v.z, w[i].z, fmaf(v.w, w[i].w, a))));
+          }
+          acc[j] = a;
+        }
+      }
+    }
+    if (slab == nslab - 1) {
+      const long long img = blockIdx.x + (seq / nslab) * gridDim.x;
+      const float inv = 1.0f / static_cast<float>(hw);
+#pragma unroll
+      for (int j = 0; j < kPoolMaxAcc / 4; ++j) {
+        const int e = t + kPoolThreads * j;
+        if (e < E) pooled[img * E + e] = acc[j] * inv;
+        acc[j] = 0.f;
+      }
+    }
+    __syncthreads();  // everyone is done with `cur` (and part/rn_s) before the buffer is refilled
+  }
+}
+
 int project_ncta() {
   static const int forced = [] {
     const char* e = getenv("ISX_PROJECT_CTA_PAIR");
@@ -629,12 +737,28 @@ int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, 
   int sms = 148;
   int rc = device_sm_count(&sms);
   if (rc != ISX_OK) return rc;
-  const size_t smem = static_cast<size_t>(2) * E * kSlabCells * sizeof(float);
-  ISX_CHECK_CUDA(cudaFuncSetAttribute(l2norm_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int per_sm = std::max<int>(1, static_cast<int>((220 * 1024) / (smem + 2048)));
-  const int grid = std::min(B, sms * per_sm);
-  l2norm_pool_kernel<<<grid, kPoolThreads, smem, stream>>>(fmap, B, E, static_cast<int>(hw), pooled);
-  ISX_CHECK_CUDA(cudaGetLastError());
+  if (hw % 4 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15u) == 0) {
+    // TMA-staged slabs
+    CUtensorMap tm;
+    rc = encode_tmap_3d(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, fmap, static_cast<uint64_t>(hw), static_cast<uint64_t>(E),
+                        static_cast<uint64_t>(B), static_cast<uint64_t>(hw) * 4, static_cast<uint64_t>(E) * hw * 4,
+                        kSlabCells, kPoolFeatBox, 1, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != ISX_OK) return rc;
+    const int nbox = (E + kPoolFeatBox - 1) / kPoolFeatBox;
+    const size_t smem = static_cast<size_t>(2) * nbox * kPoolFeatBox * kSlabCells * sizeof(float) + 128;
+    ISX_CHECK_CUDA(cudaFuncSetAttribute(l2norm_pool_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    const int grid = std::min(B, sms);
+    l2norm_pool_tma_kernel<<<grid, kPoolThreads, smem, stream>>>(tm, B, E, static_cast<int>(hw), pooled);
+    ISX_CHECK_CUDA(cudaGetLastError());
+  } else {
+    const size_t smem = static_cast<size_t>(2) * E * kSlabCells * sizeof(float);
+    ISX_CHECK_CUDA(cudaFuncSetAttribute(l2norm_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int per_sm = std::max<int>(1, static_cast<int>((220 * 1024) / (smem + 2048)));
+    const int grid = std::min(B, sms * per_sm);
+    l2norm_pool_kernel<<<grid, kPoolThreads, smem, stream>>>(fmap, B, E, static_cast<int>(hw), pooled);
+    ISX_CHECK_CUDA(cudaGetLastError());
+  }
   // project the pooled rows: an n x F matrix is a feature "map" with one cell per image
   return launch_project(pooled, B, E, 1, k, /*normalize=*/0, packed, out, stream, fn);
 }
