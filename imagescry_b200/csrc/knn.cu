@@ -221,7 +221,9 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   const long long unit = blockIdx.x / NCTA, num_units = gridDim.x / NCTA;
   constexpr int E = CAP / 32;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by offsetting the shared array itself (not through an integer round trip) so the compiler
+  // keeps the shared address space and emits LDS/STS instead of generic loads and stores
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   if (threadIdx.x == 0 && static_cast<uint32_t>(smem - smem_raw) + L::kTotal > L::kDynamicBytes) {
     printf("isx: knn_search_kernel: dynamic shared memory window is not 1024-byte aligned\n");
     __trap();

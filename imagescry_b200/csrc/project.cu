@@ -48,21 +48,29 @@ constexpr int P_ACC_STAGES = 2;
 // NCTA == 2 (CTA pair, cta_group::2): each CTA transforms its own 128 cells but stages only half of
 // the weight rows of every k-block, so the L2 -> shared-memory weight stream per SM halves and the
 // freed shared memory buys a third stage for both rings.
-template <int NCTA>
+// STAGED (pairs only): the raw fp32 128-cell x 64-feature boxes of the map arrive by TMA into a
+// two-deep ring (64 KB in flight per SM, no registers involved); the transform warps read them
+// from shared memory.  The weight ring keeps three stages, the converted-operand ring two.
+template <int NCTA, bool STAGED>
 struct ProjSmem {
+  static_assert(!STAGED || NCTA == 2, "raw staging needs the shared memory a CTA pair frees");
   static constexpr uint32_t W_PART_BYTES = (kMaxComponents / NCTA) * PK * 2;  // 32 KB, or 16 KB per CTA of a pair
   static constexpr uint32_t W_STAGE_BYTES = 2 * W_PART_BYTES;                 // hi + lo
-  static constexpr int A_STAGES = (NCTA == 2) ? 3 : 2;
+  static constexpr int A_STAGES = (NCTA == 2 && !STAGED) ? 3 : 2;
   static constexpr int W_STAGES = (NCTA == 2) ? 3 : 2;
+  static constexpr int RAW_STAGES = STAGED ? 2 : 0;
+  static constexpr uint32_t RAW_STAGE_BYTES = PM * PK * 4;                   // 32 KB
   static constexpr uint32_t kAOff = 0;
-  static constexpr uint32_t kWOff = kAOff + A_STAGES * A_STAGE_BYTES_P;      // 64 KB
-  static constexpr uint32_t kSsOff = kWOff + W_STAGES * W_STAGE_BYTES;       // +128 KB
-  static constexpr uint32_t kBiasOff = kSsOff + P_ACC_STAGES * 2 * PM * 4;   // [acc][half][row]
-  static constexpr uint32_t kBarOff = kBiasOff + kMaxComponents * 4;
-  static constexpr uint32_t kNumBars = 2 * A_STAGES + 2 * W_STAGES + 4 * P_ACC_STAGES;
+  static constexpr uint32_t kWOff = kAOff + A_STAGES * A_STAGE_BYTES_P;
+  static constexpr uint32_t kRawOff = kWOff + W_STAGES * W_STAGE_BYTES;
+  static constexpr uint32_t kSsOff = kRawOff + RAW_STAGES * RAW_STAGE_BYTES;
+  static constexpr uint32_t kBarOff = kSsOff + P_ACC_STAGES * 2 * PM * 4;    // after ss[acc][half][row]
+  static constexpr uint32_t kNumBars = 2 * A_STAGES + 2 * W_STAGES + 4 * P_ACC_STAGES + 2 * RAW_STAGES;
   static constexpr uint32_t kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr uint32_t kTotal = kTmemPtrOff + 16;
-  static constexpr uint32_t kDynamicBytes = kTotal + 1024;
+  static constexpr uint32_t kMaxDynamic = 232448;
+  static constexpr uint32_t kDynamicBytes = (kTotal + 1024 <= kMaxDynamic) ? kTotal + 1024 : kMaxDynamic;
+  static_assert(kTotal <= kMaxDynamic, "shared-memory plan exceeds 227 KB");
 };
 
 struct PackedLayout {
@@ -111,6 +119,8 @@ struct ProjParams {
   const float* fmap;
   long long m_total;  // B * hw cells (rows)
   int E, hw, k, k_pad;
+  int debug;          // TEMP experiment bits
+  int prefetch;       // 1: tmap_x describes fmap and warp 3 prefetches tiles into L2 ahead of the transform
   int normalize;
   long long tiles;
   const float* bias;
@@ -122,14 +132,21 @@ struct ProjParams {
 template <int HW, int NCTA>
 __global__ void __launch_bounds__(kProjThreads, 1)
 l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_constant__ CUtensorMap tmap_wlo,
-                      const ProjParams p) {
-  using L = ProjSmem<NCTA>;
-  constexpr int A_STAGES = L::A_STAGES, W_STAGES = L::W_STAGES;
+                      const __grid_constant__ CUtensorMap tmap_x, const ProjParams p) {
+  constexpr bool STAGED = (HW < 0);  // HW == -1: raw tiles staged by TMA (pairs only)
+  using L = ProjSmem<NCTA, STAGED>;
+  constexpr int A_STAGES = L::A_STAGES, W_STAGES = L::W_STAGES, RAW_STAGES = L::RAW_STAGES;
   constexpr uint32_t W_PART_BYTES = L::W_PART_BYTES, W_STAGE_BYTES = L::W_STAGE_BYTES;
   const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
   const long long unit = blockIdx.x / NCTA, num_units = gridDim.x / NCTA;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by offsetting the shared array itself (not through an integer round trip) so the compiler
+  // keeps the shared address space and emits LDS/STS instead of generic loads and stores
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  if (threadIdx.x == 0 && static_cast<uint32_t>(smem - smem_raw) + L::kTotal > L::kDynamicBytes) {
+    printf("isx: l2norm_project_kernel: dynamic shared memory window is not 1024-byte aligned\n");
+    __trap();
+  }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* a_full = bars;                        // [A_STAGES]  8 transform warps per CTA (on the leader)
   uint64_t* a_empty = a_full + A_STAGES;          // [A_STAGES]  tcgen05.commit
@@ -139,9 +156,10 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
   uint64_t* tmem_empty = tmem_full + P_ACC_STAGES;  // [ACC]     4 epilogue warps
   uint64_t* ss_full = tmem_empty + P_ACC_STAGES;  // [ACC]       256 transform threads
   uint64_t* ss_empty = ss_full + P_ACC_STAGES;    // [ACC]       4 epilogue warps
+  uint64_t* raw_full = ss_empty + P_ACC_STAGES;   // [RAW]       TMA (staged mode)
+  uint64_t* raw_empty = raw_full + RAW_STAGES;    // [RAW]       8 transform warps
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
   float* ss_s = reinterpret_cast<float*>(smem + L::kSsOff);
-  float* bias_s = reinterpret_cast<float*>(smem + L::kBiasOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,13 +178,13 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
       mbar_init(&ss_full[i], kTransformThreads);
       mbar_init(&ss_empty[i], 4);
     }
+    for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kTransformThreads / 32); }
     fence_mbar_init();
   }
   if (warp == 2) {
     if (NCTA == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
     else { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
   }
-  for (int i = threadIdx.x; i < kMaxComponents; i += blockDim.x) bias_s[i] = (i < p.k_pad) ? p.bias[i] : 0.f;
   tc_fence_before();
   if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -183,7 +201,9 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&w_empty[stage], phase ^ 1);
           uint8_t* dst = smem + L::kWOff + stage * W_STAGE_BYTES;
-          if (NCTA == 2) {
+          if (p.debug & 8) {
+            if (NCTA == 2) mbar_arrive_leader(&w_full[stage]); else mbar_arrive(&w_full[stage]);
+          } else if (NCTA == 2) {
             mbar_arrive_expect_tx_leader(&w_full[stage], 2 * w_part_bytes);
             tma_load_2d_pair(dst, &tmap_whi, &w_full[stage], kb * PK, row0, kEvictLast);
             tma_load_2d_pair(dst + W_PART_BYTES, &tmap_wlo, &w_full[stage], kb * PK, row0, kEvictLast);
@@ -218,6 +238,7 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
             const uint32_t o = k * P_UMMA_K * 2;
             const uint64_t dah = make_kmajor_sw128_desc(a_hi + o), dal = make_kmajor_sw128_desc(a_lo + o);
             const uint64_t dwh = make_kmajor_sw128_desc(w_hi + o), dwl = make_kmajor_sw128_desc(w_lo + o);
+            if (p.debug & 2) continue;
             if (NCTA == 2) {
               tc_mma_f16_pair(d_tmem, dah, dwh, idesc, (kb | k) != 0);
               tc_mma_f16_pair(d_tmem, dal, dwh, idesc, 1);
@@ -237,6 +258,51 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
         if (++acc == P_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ===================== L2 prefetcher =====================
+    // The transform warps can keep only one k-block of loads in flight (registers); this lane asks
+    // the TMA unit to pull whole 128-cell x 64-feature boxes of the map into L2 kPrefetchDepth
+    // k-blocks ahead, paced by the same a_empty barriers the transform waits on, so that those loads
+    // find their lines in L2 instead of HBM.
+    if (STAGED) {
+      // ===================== raw-tile TMA producer (staged mode) =====================
+      if (lane == 0) {
+        uint32_t rs = 0, rph = 0;
+        for (long long tile = unit; tile < p.tiles; tile += num_units) {
+          const long long R0 = (tile * NCTA + rank) * PM;
+          const long long img = R0 / p.hw;
+          const int cell = static_cast<int>(R0 - img * p.hw);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&raw_empty[rs], rph ^ 1);
+            mbar_arrive_expect_tx(&raw_full[rs], L::RAW_STAGE_BYTES);
+            tma_load_3d(smem + L::kRawOff + rs * L::RAW_STAGE_BYTES, &tmap_x, &raw_full[rs], cell, kb * PK,
+                        static_cast<int32_t>(img), kEvictFirst);
+            if (++rs == static_cast<uint32_t>(RAW_STAGES)) { rs = 0; rph ^= 1; }
+          }
+        }
+      }
+    } else if (lane == 0 && p.prefetch) {
+      constexpr int kPrefetchDepth = 6;
+      const long long my_tiles = (p.tiles - unit + num_units - 1) / num_units;
+      const long long total_seq = my_tiles * num_kb;
+      auto prefetch = [&](long long seq) {
+        const long long tile_iter = seq / num_kb;
+        const int kb = static_cast<int>(seq - tile_iter * num_kb);
+        const long long R0 = ((unit + tile_iter * num_units) * NCTA + rank) * PM;
+        if (R0 >= p.m_total) return;
+        const long long img = R0 / p.hw;
+        const int cell = static_cast<int>(R0 - img * p.hw);
+        asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                         reinterpret_cast<uint64_t>(&tmap_x)),
+                     "r"(cell), "r"(kb * PK), "r"(static_cast<int32_t>(img))
+                     : "memory");
+      };
+      for (long long s2 = 0; s2 < kPrefetchDepth && s2 < total_seq; ++s2) prefetch(s2);
+      for (long long seq = 0; seq + kPrefetchDepth < total_seq; ++seq) {
+        mbar_wait(&a_empty[seq % A_STAGES], static_cast<uint32_t>(((seq / A_STAGES) & 1) ^ 1));
+        prefetch(seq + kPrefetchDepth);
+      }
+    }
   } else if (warp >= kTransformWarp0) {
     // ===================== transform: fp32 NCHW -> bf16 hi/lo K-major tiles =====================
     const int t = threadIdx.x - kTransformWarp0 * 32;  // 0..255
@@ -245,44 +311,56 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
     const long long my_tiles = (p.tiles - unit + num_units - 1) / num_units;
     const long long total_seq = my_tiles * num_kb;
 
-    auto row_base = [&](long long tile_iter, bool& valid) -> const float* {
+    // Two cursors walk the flattened (tile, k-block) sequence without any division: `ld` issues the
+    // global loads one k-block ahead of `pr`, which converts and publishes the operand tiles.
+    struct Cursor {
+      long long tile_iter;
+      int kb;
+    };
+    Cursor ld = {0, 0};
+    const float* ld_base = nullptr;  // &fmap[img][0][cell] of this thread's row in ld's tile
+    bool ld_valid = false;
+    auto seek_tile = [&](long long tile_iter) {
       const long long tile = unit + tile_iter * num_units;
       const long long R = (tile * NCTA + rank) * PM + m;
-      valid = R < p.m_total;
-      const long long img = valid ? R / p.hw : 0;
-      const long long cell = valid ? R - img * p.hw : 0;
-      return p.fmap + img * p.E * static_cast<long long>(p.hw) + cell;
+      ld_valid = tile_iter < my_tiles && R < p.m_total;
+      const long long img = ld_valid ? R / p.hw : 0;  // once per tile
+      const long long cell = ld_valid ? R - img * p.hw : 0;
+      ld_base = p.fmap + img * p.E * static_cast<long long>(p.hw) + cell;
     };
-    auto load_block = [&](float (&x)[32], long long seq) {
-      const long long tile_iter = seq / num_kb;
-      const int kb = static_cast<int>(seq - tile_iter * num_kb);
-      bool valid;
-      const float* base = row_base(tile_iter, valid);
-      const int f0 = kb * PK + half * 32;
+    seek_tile(0);
+    auto ld_f32 = [](const float* ptr) {
+      float v;
+      asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+      return v;
+    };
+    auto load_block = [&](float (&x)[32]) {
+      const int f0 = ld.kb * PK + half * 32;
       if (HW > 0) {
         // E % 64 == 0: every feature of the block exists; channel stride is a compile-time constant
-        const float* src = base + static_cast<long long>(f0) * HW;
-        if (valid) {
+        const float* src = ld_base + static_cast<long long>(f0) * HW;
+        if (ld_valid && !(p.debug & 1)) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = __ldg(src + i * HW);
+          for (int i = 0; i < 32; ++i) x[i] = ld_f32(src + i * HW);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = 0.f;
         }
       } else {
+        const float* src = ld_base + static_cast<long long>(f0) * p.hw;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int f = f0 + i;
-          x[i] = (valid && f < p.E) ? __ldg(base + static_cast<long long>(f) * p.hw) : 0.f;
+          x[i] = (ld_valid && f0 + i < p.E) ? ld_f32(src) : 0.f;
+          src += p.hw;
         }
       }
+      if (++ld.kb == num_kb) { ld.kb = 0; seek_tile(++ld.tile_iter); }
     };
 
     float ss = 0.f;
-    uint32_t acc = 0, acc_phase = 0;
-    auto process = [&](float (&x)[32], long long seq) {
-      const uint32_t stage = static_cast<uint32_t>(seq % A_STAGES);
-      const uint32_t phase = static_cast<uint32_t>((seq / A_STAGES) & 1);
+    uint32_t acc = 0, acc_phase = 0, stage = 0, phase = 0;
+    int pr_kb = 0;
+    auto process = [&](float (&x)[32]) {
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -312,9 +390,10 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
       if (lane == 0) {
         if (NCTA == 2) mbar_arrive_leader(&a_full[stage]); else mbar_arrive(&a_full[stage]);
       }
-      const long long tile_iter = seq / num_kb;
-      if (seq - tile_iter * num_kb == num_kb - 1) {
+      if (++stage == static_cast<uint32_t>(A_STAGES)) { stage = 0; phase ^= 1; }
+      if (++pr_kb == num_kb) {
         // last k-block of the tile: publish this thread's share of the row's sum of squares
+        pr_kb = 0;
         mbar_wait(&ss_empty[acc], acc_phase ^ 1);
         ss_s[(acc * 2 + half) * PM + m] = ss;
         mbar_arrive(&ss_full[acc]);
@@ -323,14 +402,32 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
       }
     };
 
-    float xa[32], xb[32];
-    if (total_seq > 0) load_block(xa, 0);
-    for (long long seq = 0; seq < total_seq; seq += 2) {
-      if (seq + 1 < total_seq) load_block(xb, seq + 1);
-      process(xa, seq);
-      if (seq + 1 < total_seq) {
-        if (seq + 2 < total_seq) load_block(xa, seq + 2);
-        process(xb, seq + 1);
+    if constexpr (STAGED) {
+      // raw box layout: [image][feature][cell] with cb = min(hw, 128) cells per image row
+      const int cb = min(p.hw, PM);
+      const int m_off = (m / cb) * (PK * cb) + (m % cb) + half * 32 * cb;
+      uint32_t rs = 0, rph = 0;
+      for (long long seq = 0; seq < total_seq; ++seq) {
+        mbar_wait(&raw_full[rs], rph);
+        const float* raw = reinterpret_cast<const float*>(smem + L::kRawOff + rs * L::RAW_STAGE_BYTES) + m_off;
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = (p.debug & 1) ? 0.f : raw[i * cb];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);  // release: this warp's reads of the stage are done
+        if (++rs == static_cast<uint32_t>(RAW_STAGES)) { rs = 0; rph ^= 1; }
+        process(x);
+      }
+    } else {
+      float xa[32], xb[32];
+      if (total_seq > 0) load_block(xa);
+      for (long long seq = 0; seq < total_seq; seq += 2) {
+        if (seq + 1 < total_seq) load_block(xb);
+        process(xa);
+        if (seq + 1 < total_seq) {
+          if (seq + 2 < total_seq) load_block(xa);
+          process(xb);
+        }
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -358,10 +455,10 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
         uint32_t r[16];
         tmem_ld_32x16(taddr + c0, r);
         tc_wait_ld();
-        if (R < p.m_total) {
+        if (R < p.m_total && !(p.debug & 4)) {
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), rn, bias_s[c0 + j]);
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), rn, __ldg(p.bias + c0 + j));
           if (vec_ok && c0 + 16 <= p.k) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -509,7 +606,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1)
 l2norm_pool_tma_kernel(const __grid_constant__ CUtensorMap tmap, int B, int E, int hw, float* __restrict__ pooled) {
   extern __shared__ uint8_t pool_tma_raw[];
   // TMA destinations need 128-byte alignment; the dynamic window follows the static arrays below
-  uint8_t* pool_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pool_tma_raw) + 127) & ~uintptr_t(127));
+  uint8_t* pool_smem = pool_tma_raw + ((128u - (smem_u32(pool_tma_raw) & 127u)) & 127u);
   __shared__ __align__(8) uint64_t full_bar[2];
   __shared__ float part[16][kSlabCells];
   __shared__ __align__(16) float rn_s[kSlabCells];
@@ -614,10 +711,10 @@ int project_ncta() {
 }
 
 template <int HW, int NCTA>
-int launch_project_kernel(const CUtensorMap& twh, const CUtensorMap& twl, const ProjParams& p, int grid,
-                          cudaStream_t stream) {
+int launch_project_kernel(const CUtensorMap& twh, const CUtensorMap& twl, const CUtensorMap& tx, const ProjParams& p,
+                          int grid, cudaStream_t stream) {
   auto kern = l2norm_project_kernel<HW, NCTA>;
-  const int smem = static_cast<int>(ProjSmem<NCTA>::kDynamicBytes);
+  const int smem = static_cast<int>(ProjSmem<NCTA, (HW < 0)>::kDynamicBytes);
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -631,7 +728,7 @@ int launch_project_kernel(const CUtensorMap& twh, const CUtensorMap& twl, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ISX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, twh, twl, p));
+  ISX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, twh, twl, tx, p));
   return ISX_OK;
 }
 
@@ -659,9 +756,28 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
   p.bias = reinterpret_cast<const float*>(pk + l.bias_off);
   p.out = out;
   const int grid = static_cast<int>(std::min<long long>(sms / NCTA, p.tiles)) * NCTA;
-  if (E % PK == 0 && hw == 256) return launch_project_kernel<256, NCTA>(twh, twl, p, grid, stream);
-  if (E % PK == 0 && hw == 64) return launch_project_kernel<64, NCTA>(twh, twl, p, grid, stream);
-  return launch_project_kernel<0, NCTA>(twh, twl, p, grid, stream);
+  // L2 prefetch boxes: a tile of 128 cells is half/quarter/... of one image (hw % 128 == 0) or a
+  // whole number of images (128 % hw == 0); other shapes run without the prefetcher
+  CUtensorMap tx = twh;
+  p.prefetch = 0;
+  p.debug = getenv("ISX_PROJECT_DEBUG") ? atoi(getenv("ISX_PROJECT_DEBUG")) : 0;
+  const long long images = m_total / hw;
+  if (hw % 4 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15u) == 0 && (hw % PM == 0 || PM % hw == 0) && images >= 1) {
+    const uint32_t cells_box = static_cast<uint32_t>(std::min(hw, PM));
+    const uint32_t imgs_box = static_cast<uint32_t>(PM / static_cast<int>(cells_box));
+    rc = encode_tmap_3d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, fmap, static_cast<uint64_t>(hw), static_cast<uint64_t>(E),
+                        static_cast<uint64_t>(images), static_cast<uint64_t>(hw) * 4, static_cast<uint64_t>(E) * hw * 4,
+                        cells_box, PK, imgs_box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != ISX_OK) return rc;
+    p.prefetch = 1;
+  }
+  if constexpr (NCTA == 2) {
+    static const bool staged_off = [] { const char* e = getenv("ISX_PROJECT_STAGED"); return e && e[0] == '0'; }();
+    if (p.prefetch && !staged_off) return launch_project_kernel<-1, 2>(twh, twl, tx, p, grid, stream);
+  }
+  if (E % PK == 0 && hw == 256) return launch_project_kernel<256, NCTA>(twh, twl, tx, p, grid, stream);
+  if (E % PK == 0 && hw == 64) return launch_project_kernel<64, NCTA>(twh, twl, tx, p, grid, stream);
+  return launch_project_kernel<0, NCTA>(twh, twl, tx, p, grid, stream);
 }
 
 int launch_project(const float* fmap, long long m_total, int E, int hw, int k, int normalize,
