@@ -122,16 +122,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// Suspend-time hint: the waiting thread sleeps in hardware until the phase completes (or this many
+// nanoseconds pass) instead of polling, so waiting warps do not take issue slots from working ones.
+constexpr uint32_t kMbarSuspendHintNs = 0x989680u;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHintNs)
       : "memory");
   return ok != 0;
 }

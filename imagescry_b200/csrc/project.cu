@@ -36,9 +36,11 @@ namespace {
 constexpr int PM = 128;  // cells per tile (TMEM lanes)
 constexpr int PK = 64;   // features per k-block
 constexpr int P_UMMA_K = 16;
-constexpr int kProjThreads = 512;
 constexpr int kTransformWarp0 = 8;
-constexpr int kTransformThreads = 256;
+// transform warps: 8 in the register-path kernels (32 features per thread and k-block), 16 in the
+// staged kernel (16 features per thread: twice the warps hide the LDS / barrier / fence latencies)
+constexpr int transform_warps(bool staged) { return staged ? 16 : 8; }
+constexpr int proj_threads(bool staged) { return (kTransformWarp0 + transform_warps(staged)) * 32; }
 constexpr int kMaxComponents = 256;
 
 constexpr uint32_t A_PART_BYTES = PM * PK * 2;           // 16 KB (one of hi / lo)
@@ -49,16 +51,16 @@ constexpr int P_ACC_STAGES = 2;
 // the weight rows of every k-block, so the L2 -> shared-memory weight stream per SM halves and the
 // freed shared memory buys a third stage for both rings.
 // STAGED (pairs only): the raw fp32 128-cell x 64-feature boxes of the map arrive by TMA into a
-// two-deep ring (64 KB in flight per SM, no registers involved); the transform warps read them
-// from shared memory.  The weight ring keeps three stages, the converted-operand ring two.
+// three-deep ring (96 KB in flight per SM, no registers involved); the transform warps read them
+// from shared memory.  The weight and converted-operand rings have two stages each.
 template <int NCTA, bool STAGED>
 struct ProjSmem {
   static_assert(!STAGED || NCTA == 2, "raw staging needs the shared memory a CTA pair frees");
   static constexpr uint32_t W_PART_BYTES = (kMaxComponents / NCTA) * PK * 2;  // 32 KB, or 16 KB per CTA of a pair
   static constexpr uint32_t W_STAGE_BYTES = 2 * W_PART_BYTES;                 // hi + lo
   static constexpr int A_STAGES = (NCTA == 2 && !STAGED) ? 3 : 2;
-  static constexpr int W_STAGES = (NCTA == 2) ? 3 : 2;
-  static constexpr int RAW_STAGES = STAGED ? 2 : 0;
+  static constexpr int W_STAGES = (NCTA == 2 && !STAGED) ? 3 : 2;
+  static constexpr int RAW_STAGES = STAGED ? 3 : 0;
   static constexpr uint32_t RAW_STAGE_BYTES = PM * PK * 4;                   // 32 KB
   static constexpr uint32_t kAOff = 0;
   static constexpr uint32_t kWOff = kAOff + A_STAGES * A_STAGE_BYTES_P;
@@ -119,7 +121,6 @@ struct ProjParams {
   const float* fmap;
   long long m_total;  // B * hw cells (rows)
   int E, hw, k, k_pad;
-  int debug;          // TEMP experiment bits
   int prefetch;       // 1: tmap_x describes fmap and warp 3 prefetches tiles into L2 ahead of the transform
   int normalize;
   long long tiles;
@@ -130,12 +131,13 @@ struct ProjParams {
 // HW: cells per image known at compile time (256 = 16x16, 64 = 8x8 maps: channel strides become
 // immediate load offsets), or 0 for any shape.  The fast paths also need E % 64 == 0.
 template <int HW, int NCTA>
-__global__ void __launch_bounds__(kProjThreads, 1)
+__global__ void __launch_bounds__(proj_threads(HW < 0), 1)
 l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_constant__ CUtensorMap tmap_wlo,
                       const __grid_constant__ CUtensorMap tmap_x, const ProjParams p) {
   constexpr bool STAGED = (HW < 0);  // HW == -1: raw tiles staged by TMA (pairs only)
   using L = ProjSmem<NCTA, STAGED>;
   constexpr int A_STAGES = L::A_STAGES, W_STAGES = L::W_STAGES, RAW_STAGES = L::RAW_STAGES;
+  constexpr int TW = transform_warps(STAGED);
   constexpr uint32_t W_PART_BYTES = L::W_PART_BYTES, W_STAGE_BYTES = L::W_STAGE_BYTES;
   const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
   const long long unit = blockIdx.x / NCTA, num_units = gridDim.x / NCTA;
@@ -170,15 +172,15 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
     prefetch_tmap(&tmap_wlo);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], (kTransformThreads / 32) * NCTA); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], TW * NCTA); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < W_STAGES; ++i) { mbar_init(&w_full[i], NCTA); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < P_ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4 * NCTA);
-      mbar_init(&ss_full[i], kTransformThreads);
+      mbar_init(&ss_full[i], STAGED ? TW : TW * 32);
       mbar_init(&ss_empty[i], 4);
     }
-    for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kTransformThreads / 32); }
+    for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], TW); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -201,9 +203,7 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&w_empty[stage], phase ^ 1);
           uint8_t* dst = smem + L::kWOff + stage * W_STAGE_BYTES;
-          if (p.debug & 8) {
-            if (NCTA == 2) mbar_arrive_leader(&w_full[stage]); else mbar_arrive(&w_full[stage]);
-          } else if (NCTA == 2) {
+          if (NCTA == 2) {
             mbar_arrive_expect_tx_leader(&w_full[stage], 2 * w_part_bytes);
             tma_load_2d_pair(dst, &tmap_whi, &w_full[stage], kb * PK, row0, kEvictLast);
             tma_load_2d_pair(dst + W_PART_BYTES, &tmap_wlo, &w_full[stage], kb * PK, row0, kEvictLast);
@@ -238,7 +238,6 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
             const uint32_t o = k * P_UMMA_K * 2;
             const uint64_t dah = make_kmajor_sw128_desc(a_hi + o), dal = make_kmajor_sw128_desc(a_lo + o);
             const uint64_t dwh = make_kmajor_sw128_desc(w_hi + o), dwl = make_kmajor_sw128_desc(w_lo + o);
-            if (p.debug & 2) continue;
             if (NCTA == 2) {
               tc_mma_f16_pair(d_tmem, dah, dwh, idesc, (kb | k) != 0);
               tc_mma_f16_pair(d_tmem, dal, dwh, idesc, 1);
@@ -305,11 +304,74 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
     }
   } else if (warp >= kTransformWarp0) {
     // ===================== transform: fp32 NCHW -> bf16 hi/lo K-major tiles =====================
+    const long long my_tiles = (p.tiles - unit + num_units - 1) / num_units;
+    const long long total_seq = my_tiles * num_kb;
+    if constexpr (STAGED) {
+      // 16 warps.  Warp tw: rows 16 (tw % 8) .. +15; lanes 0-15 take feature quarter 2 (tw / 8),
+      // lanes 16-31 the next quarter of the same rows (one shuffle then sums the two quarters'
+      // sums of squares).  Raw box layout: [image][feature][cell], cb = min(hw, 128) cells per row.
+      const int tw = warp - kTransformWarp0;
+      const int m = (tw & 7) * 16 + (lane & 15);
+      const int quarter = (tw >> 3) * 2 + (lane >> 4);
+      const int cb = min(p.hw, PM);
+      const int m_off = (m / cb) * (PK * cb) + (m % cb) + quarter * 16 * cb;
+      float ss = 0.f;
+      uint32_t acc = 0, acc_phase = 0, stage = 0, phase = 0, rs = 0, rph = 0;
+      int pr_kb = 0;
+      for (long long seq = 0; seq < total_seq; ++seq) {
+        mbar_wait(&raw_full[rs], rph);
+        const float* raw = reinterpret_cast<const float*>(smem + L::kRawOff + rs * L::RAW_STAGE_BYTES) + m_off;
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = raw[i * cb];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);  // release: this warp's reads of the stage are done
+        if (++rs == static_cast<uint32_t>(RAW_STAGES)) { rs = 0; rph ^= 1; }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = x[2 * i], b = x[2 * i + 1];
+          ss = fmaf(a, a, ss);
+          ss = fmaf(b, b, ss);
+          // hi = x truncated to bf16 (a mask); lo = RN_bf16(x - hi): |x - hi - lo| <= 2^-16 |x|
+          const uint32_t ab = __float_as_uint(a), bb = __float_as_uint(b);
+          hi[i] = __byte_perm(ab, bb, 0x7632);
+          const float la = a - __uint_as_float(ab & 0xFFFF0000u);
+          const float lb = b - __uint_as_float(bb & 0xFFFF0000u);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(la, lb);
+          lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        uint8_t* a_hi = smem + L::kAOff + stage * A_STAGE_BYTES_P + m * 128;
+        uint8_t* a_lo = a_hi + A_PART_BYTES;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int chunk = (quarter * 2 + c) ^ (m & 7);  // 128B swizzle: 16-byte chunk index XOR row % 8
+          *reinterpret_cast<uint4*>(a_hi + chunk * 16) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+          *reinterpret_cast<uint4*>(a_lo + chunk * 16) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_leader(&a_full[stage]); else mbar_arrive(&a_full[stage]);
+        }
+        if (++stage == static_cast<uint32_t>(A_STAGES)) { stage = 0; phase ^= 1; }
+        if (++pr_kb == num_kb) {
+          // last k-block of the tile: publish the row's sum of squares over this warp's two quarters
+          pr_kb = 0;
+          const float both = ss + __shfl_xor_sync(kFullMask, ss, 16);
+          mbar_wait(&ss_empty[acc], acc_phase ^ 1);
+          if (lane < 16) ss_s[(acc * 2 + (tw >> 3)) * PM + m] = both;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ss_full[acc]);
+          ss = 0.f;
+          if (++acc == P_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    } else {
     const int t = threadIdx.x - kTransformWarp0 * 32;  // 0..255
     const int m = t & (PM - 1);                        // row (cell) inside the tile
     const int half = t >> 7;                           // which 32 of the k-block's 64 features
-    const long long my_tiles = (p.tiles - unit + num_units - 1) / num_units;
-    const long long total_seq = my_tiles * num_kb;
 
     // Two cursors walk the flattened (tile, k-block) sequence without any division: `ld` issues the
     // global loads one k-block ahead of `pr`, which converts and publishes the operand tiles.
@@ -339,7 +401,7 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
       if (HW > 0) {
         // E % 64 == 0: every feature of the block exists; channel stride is a compile-time constant
         const float* src = ld_base + static_cast<long long>(f0) * HW;
-        if (ld_valid && !(p.debug & 1)) {
+        if (ld_valid) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = ld_f32(src + i * HW);
         } else {
@@ -402,34 +464,17 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
       }
     };
 
-    if constexpr (STAGED) {
-      // raw box layout: [image][feature][cell] with cb = min(hw, 128) cells per image row
-      const int cb = min(p.hw, PM);
-      const int m_off = (m / cb) * (PK * cb) + (m % cb) + half * 32 * cb;
-      uint32_t rs = 0, rph = 0;
-      for (long long seq = 0; seq < total_seq; ++seq) {
-        mbar_wait(&raw_full[rs], rph);
-        const float* raw = reinterpret_cast<const float*>(smem + L::kRawOff + rs * L::RAW_STAGE_BYTES) + m_off;
-        float x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = (p.debug & 1) ? 0.f : raw[i * cb];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[rs]);  // release: this warp's reads of the stage are done
-        if (++rs == static_cast<uint32_t>(RAW_STAGES)) { rs = 0; rph ^= 1; }
-        process(x);
-      }
-    } else {
-      float xa[32], xb[32];
-      if (total_seq > 0) load_block(xa);
-      for (long long seq = 0; seq < total_seq; seq += 2) {
-        if (seq + 1 < total_seq) load_block(xb);
-        process(xa);
-        if (seq + 1 < total_seq) {
-          if (seq + 2 < total_seq) load_block(xa);
-          process(xb);
-        }
+    float xa[32], xb[32];
+    if (total_seq > 0) load_block(xa);
+    for (long long seq = 0; seq < total_seq; seq += 2) {
+      if (seq + 1 < total_seq) load_block(xb);
+      process(xa);
+      if (seq + 1 < total_seq) {
+        if (seq + 2 < total_seq) load_block(xa);
+        process(xb);
       }
     }
+    }  // register path
   } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue =====================
     const int ew = warp - 4;  // == warp % 4: TMEM lane quarter
@@ -455,7 +500,7 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
         uint32_t r[16];
         tmem_ld_32x16(taddr + c0, r);
         tc_wait_ld();
-        if (R < p.m_total && !(p.debug & 4)) {
+        if (R < p.m_total) {
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), rn, __ldg(p.bias + c0 + j));
@@ -718,7 +763,7 @@ int launch_project_kernel(const CUtensorMap& twh, const CUtensorMap& twl, const 
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(kProjThreads);
+  cfg.blockDim = dim3(proj_threads(HW < 0));
   cfg.dynamicSmemBytes = static_cast<size_t>(smem);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -760,7 +805,6 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
   // whole number of images (128 % hw == 0); other shapes run without the prefetcher
   CUtensorMap tx = twh;
   p.prefetch = 0;
-  p.debug = getenv("ISX_PROJECT_DEBUG") ? atoi(getenv("ISX_PROJECT_DEBUG")) : 0;
   const long long images = m_total / hw;
   if (hw % 4 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15u) == 0 && (hw % PM == 0 || PM % hw == 0) && images >= 1) {
     const uint32_t cells_box = static_cast<uint32_t>(std::min(hw, PM));
