@@ -53,6 +53,17 @@ def load_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
 
 
+def load_traffic():
+    """DRAM bytes per launch of the search kernel (dram__bytes_read.sum + dram__bytes_write.sum) from
+    the committed `ncu --set full` capture of this same workload, or None."""
+    path = os.path.join(REPO, "profiles", "knn_search_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
 
@@ -421,7 +432,7 @@ def run_b200(args) -> None:
     peak_sus = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus,
-        "traffic": None, "kernel": "knn_search_kernel<64> (+ topk_merge, <1 % of the interval)", "kernel_ms": k_ms,
+        "traffic": load_traffic(), "kernel": "knn_search_kernel<32, 2> (CTA pairs; + topk_merge, <1 % of the interval)", "kernel_ms": k_ms,
         "flops_per_launch": flops, "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside the step loop)",
         "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
     }

@@ -116,6 +116,57 @@ row_rnorm_kernel(const __nv_bfloat16* __restrict__ x, long long n, int d, float 
 }
 
 // ------------------------------------------------------------------------------------------
+// Store build from the reference's embedding BLOB layout (storage/models.py:94-129: float32 C x H x W,
+// C-order): maps N x C x hw  ->  bf16 rows.  pool == 0: one row per cell, (N * hw) x C, i.e. the
+// get_flat_vectors order of data.py:112-118; pool == 1: the spatial mean, N x C.
+// 32 x 32 tiles go through shared memory so that both the reads (along hw) and the writes (along C)
+// are coalesced.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maps_to_rows_kernel(const float* __restrict__ maps, long long n, int C, int hw, __nv_bfloat16* __restrict__ rows) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int ctiles = (C + 31) / 32, stiles = (hw + 31) / 32;
+  const long long per_img = static_cast<long long>(ctiles) * stiles;
+  const long long total = per_img * n;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const long long img = t / per_img;
+    const int rem = static_cast<int>(t - img * per_img);
+    const int c0 = (rem / stiles) * 32, s0 = (rem % stiles) * 32;
+    const float* src = maps + img * C * static_cast<long long>(hw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + ty + 8 * j, sidx = s0 + tx;
+      tile[ty + 8 * j][tx] = (c < C && sidx < hw) ? src[static_cast<long long>(c) * hw + sidx] : 0.f;
+    }
+    __syncthreads();
+    __nv_bfloat16* dst = rows + (img * hw) * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sidx = s0 + ty + 8 * j, c = c0 + tx;
+      if (sidx < hw && c < C) dst[static_cast<long long>(sidx) * C + c] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
+    }
+    __syncthreads();
+  }
+}
+
+// one warp per (image, channel): fp32 sum over the cells in a fixed order, / hw, rounded to bf16
+__global__ void __launch_bounds__(256)
+maps_pool_rows_kernel(const float* __restrict__ maps, long long n, int C, int hw, __nv_bfloat16* __restrict__ rows) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long total = n * C;
+  for (long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < total; r += warps) {
+    const float* src = maps + r * hw;
+    float acc = 0.f;
+    for (int i = lane; i < hw; i += 32) acc += src[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+    if (lane == 0) rows[r] = __float2bfloat16_rn(acc / static_cast<float>(hw));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K4: search
 // ------------------------------------------------------------------------------------------
 struct KnnParams {
@@ -613,6 +664,29 @@ int isx_row_rnorm_bf16(const void* x, int64_t n, int d, float eps, float* rnorm,
   const long long want = (n + 7) / 8;
   const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(sms) * 16)));
   row_rnorm_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), n, d, eps, rnorm);
+  ISX_CHECK_CUDA(cudaGetLastError());
+  return ISX_OK;
+}
+
+int isx_maps_to_rows_bf16(const float* maps, int64_t n, int C, int hw, int pool, void* rows, isx_stream_t stream_) {
+  const char* fn = "isx_maps_to_rows_bf16";
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ISX_REQUIRE(n >= 0 && C > 0 && hw > 0, "%s: need n >= 0, C > 0, hw > 0 (n=%lld C=%d hw=%d)", fn, (long long)n, C, hw);
+  ISX_REQUIRE(pool == 0 || pool == 1, "%s: pool must be 0 or 1 (got %d)", fn, pool);
+  if (n == 0) return ISX_OK;
+  ISX_REQUIRE(maps && rows, "%s: null pointer", fn);
+  int sms = 148;
+  int rc = device_sm_count(&sms);
+  if (rc != ISX_OK) return rc;
+  if (pool) {
+    const long long want = (n * C + 7) / 8;
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(sms) * 16)));
+    maps_pool_rows_kernel<<<blocks, 256, 0, stream>>>(maps, n, C, hw, static_cast<__nv_bfloat16*>(rows));
+  } else {
+    const long long tiles = static_cast<long long>((C + 31) / 32) * ((hw + 31) / 32) * n;
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(tiles, static_cast<long long>(sms) * 16)));
+    maps_to_rows_kernel<<<blocks, 256, 0, stream>>>(maps, n, C, hw, static_cast<__nv_bfloat16*>(rows));
+  }
   ISX_CHECK_CUDA(cudaGetLastError());
   return ISX_OK;
 }

@@ -121,6 +121,13 @@ int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, 
 /* rnorm[i] = 1 / max(||x_i||_2, eps) for the rows of a bf16 matrix n x d (fp32 accumulation). */
 int isx_row_rnorm_bf16(const void* x, int64_t n, int d, float eps, float* rnorm, isx_stream_t stream);
 
+/* Store build from the reference's embedding BLOBs (storage/models.py:94-129: float32, C-order
+ * C x H x W; bulk read storage/operations.py:108-144).  maps: fp32 n x C x hw (hw = H*W).
+ * pool == 0: rows = bf16 (n*hw) x C, one row per feature-map cell in data.py:112-118's
+ *            get_flat_vectors order (row = image * hw + cell);
+ * pool == 1: rows = bf16 n x C, the spatial mean of every map. */
+int isx_maps_to_rows_bf16(const float* maps, int64_t n, int C, int hw, int pool, void* rows, isx_stream_t stream);
+
 size_t isx_knn_workspace_bytes(int64_t n, int q, int d, int k);
 
 /* store: bf16 n x d row-major; queries: bf16 q x d row-major; *_rnorm from isx_row_rnorm_bf16.

@@ -364,3 +364,25 @@ def topk_merge(scores: np.ndarray, idx: np.ndarray, k: int):
     i_sort = np.where(pad, np.iinfo(np.int64).max, i)
     order = np.lexsort((i_sort, -s), axis=1)[:, :k]
     return np.take_along_axis(s, order, axis=1), np.take_along_axis(i, order, axis=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# Embedding-store wire format (storage/models.py:94-129) and the rows a search store is built from
+# ------------------------------------------------------------------------------------------------
+def blob_encode(embedding: np.ndarray) -> bytes:
+    """`Embedding.create` (storage/models.py:128): the raw bytes of a float32 C-order C×H×W array."""
+    return np.ascontiguousarray(embedding, dtype=np.float32).tobytes()
+
+
+def blob_decode(data: bytes, dim: int, height: int, width: int) -> np.ndarray:
+    """`Embedding.embedding_tensor` (storage/models.py:98-102)."""
+    return np.frombuffer(data, dtype=np.float32).reshape(dim, height, width).copy()
+
+
+def maps_to_rows(maps: np.ndarray, pool: str | None = None) -> np.ndarray:
+    """N×C×H×W float32 maps -> bf16-rounded search rows: one per cell in `get_flat_vectors` order
+    (data.py:112-118), or the spatial mean per image (pool="mean"; parity unpinned)."""
+    n, c, h, w = maps.shape
+    if pool == "mean":
+        return bf16_round(maps.reshape(n, c, h * w).astype(np.float64).mean(axis=2).astype(np.float32))
+    return bf16_round(flat_vectors(maps.astype(np.float32)))

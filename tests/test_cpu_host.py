@@ -191,3 +191,28 @@ def test_sharded_gather_plumbing_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK {r}" in o, o
+
+
+def test_store_format_codec_matches_reference_wire_format():
+    """storage/models.py:94-129: float32 C-order bytes; decode(encode(x)) == x and the byte string
+    equals numpy's tobytes() of the C×H×W array (what `Embedding.create` writes)."""
+    import numpy as np
+    import torch
+
+    from imagescry_b200 import store_format as F
+    from oracle import oracle as O
+
+    x = torch.arange(2 * 3 * 4, dtype=torch.float32).reshape(2, 3, 4) * 0.5
+    data, c, h, w = F.encode_embedding_blob(x)
+    assert (c, h, w) == (2, 3, 4) and data == x.numpy().tobytes() == O.blob_encode(x.numpy())
+    assert torch.equal(F.decode_embedding_blob(data, c, h, w), x)
+    stacked = F.stack_blobs([(data, c, h, w)] * 3)
+    assert stacked.shape == (3, 2, 3, 4)
+    import pytest
+
+    with pytest.raises(ValueError):
+        F.stack_blobs([])
+    with pytest.raises(RuntimeError):
+        F.maps_to_rows(stacked)  # CPU tensor: the conversion runs on the GPU only
+    img, cell = F.rows_to_image_cell([0, 11, 12, 25], 12)
+    assert img.tolist() == [0, 0, 1, 2] and cell.tolist() == [0, 11, 0, 1]

@@ -160,3 +160,32 @@ def test_self_search_property_large():
     sn = torch.nn.functional.normalize(store.float(), dim=1)
     ref = (sn[rows] @ sn.T).topk(10, dim=1)
     assert torch.allclose(scores, ref.values, atol=SCORE_TOL)
+
+
+def test_store_format_bridge_blobs_to_search():
+    """storage/models.py:94-129 BLOBs -> device store -> search: rows equal the oracle's bf16 rows
+    bit for bit, and a query built from one cell finds that (image, cell)."""
+    from imagescry_b200 import store_format as F
+
+    rng = np.random.default_rng(9)
+    maps = rng.standard_normal((7, 72, 5, 6)).astype(np.float32)  # C not a multiple of 32, hw = 30
+    records = [(O.blob_encode(m), 72, 5, 6) for m in maps]
+    # codec round trip equals the reference's own decode
+    for (data, c, h, w), m in zip(records, maps):
+        assert np.array_equal(F.decode_embedding_blob(data, c, h, w).numpy(), O.blob_decode(data, c, h, w))
+        assert F.encode_embedding_blob(torch.from_numpy(m))[0] == data
+    stacked = F.stack_blobs(records)
+    rows = F.maps_to_rows(stacked.cuda())
+    assert np.array_equal(rows.float().cpu().numpy(), O.maps_to_rows(maps))
+    pooled = F.maps_to_rows(stacked.cuda(), pool="mean").float().cpu().numpy()
+    ref_pooled = O.maps_to_rows(maps, pool="mean")
+    assert np.abs(pooled - ref_pooled).max() <= np.abs(ref_pooled).max() * 2.0**-7  # one bf16 ulp
+    store = F.store_from_blobs(records)
+    assert len(store) == 7 * 30 and store.dim == 72
+    q = torch.from_numpy(maps[4, :, 2, 3]).reshape(1, -1).cuda()
+    scores, idx = store.search(q, 3)
+    img, cell = F.rows_to_image_cell(idx[0, :1].cpu(), 30)
+    assert (int(img), int(cell)) == (4, 2 * 6 + 3) and abs(float(scores[0, 0]) - 1.0) < 1e-2
+    check(O.maps_to_rows(maps), O.bf16_round(maps[4, :, 2, 3].reshape(1, -1)), 3, scores, idx)
+    with pytest.raises(ValueError):
+        F.decode_embedding_blob(records[0][0], 72, 5, 5)
