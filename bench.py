@@ -80,32 +80,43 @@ class ClockSampler:
         self._thread: threading.Thread | None = None
 
     def _run(self) -> None:
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5,
-                ).stdout.strip()
-                if out:
-                    self.samples.append([v.strip() for v in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        # one long-lived nvidia-smi streaming a sample every 100 ms (spawning it per sample takes
+        # longer than a whole timed region)
+        try:
+            self._proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except Exception:
+            self._proc = None
+            return
+        for line in self._proc.stdout:  # ends when __exit__ terminates the process
+            line = line.strip()
+            if line:
+                self.samples.append([v.strip() for v in line.split(",")])
 
     def __enter__(self):
+        self._proc = None
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
+        time.sleep(0.35)  # let the first samples arrive before the timed region starts
+        self._n_before = len(self.samples)
         return self
 
     def __exit__(self, *exc):
         self._stop.set()
+        if self._proc is not None:
+            try:
+                self._proc.terminate()
+            except Exception:
+                pass
         if self._thread:
-            self._thread.join(timeout=6)
+            self._thread.join(timeout=3)
 
     def summary(self) -> dict:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in self.samples[getattr(self, "_n_before", 0):] or self.samples:
             try:
                 sm.append(float(s[0]))
                 mx.append(float(s[1]))
