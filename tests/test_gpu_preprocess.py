@@ -86,7 +86,10 @@ CASES = [
     (2, 3, 30, 45, None),       # odd plane → staged path
     (5, 1, 32, 48, None),
     (2, 4, 16, 16, None),
-    (3, 3, 64, 64, (32, 32)),   # exact 2x down-scale
+    (3, 3, 64, 64, (32, 32)),   # exact 2x down-scale: integer box path
+    (2, 3, 48, 72, (24, 36)),   # box path (NHWC), rectangular; NCHW needs outW % 8 == 0
+    (3, 3, 32, 80, (16, 40)),   # box path in both layouts
+    (2, 3, 20, 44, (10, 22)),   # 2x but outW % 4 != 0: generic sampling kernel
     (2, 3, 96, 80, (37, 31)),
     (2, 3, 40, 48, (80, 96)),   # up-scale
     (1, 3, 200, 300, (64, 96)),
@@ -156,6 +159,28 @@ def test_preprocess_float_input_and_stats_ulps():
     # float16 / int32 inputs follow the reference's `.float()` cast
     xi = rng.integers(-1000, 1000, (2, 2, 8, 8)).astype(np.int32)
     assert np.array_equal(host(T.normalize_per_channel(dev(xi))), O.normalize_per_channel(xi))
+
+
+def test_box_path_statistics_exact_large_batch():
+    """2x down-scale statistics are exact integer sums of the four taps: compare with an int64 /
+    fp64 truth at a size where fp32 or even naive fp64 accumulation orders could differ."""
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 256, (48, 128, 128, 3), dtype=np.uint8)
+    S = (x[:, 0::2, 0::2].astype(np.int64) + x[:, 0::2, 1::2] + x[:, 1::2, 0::2] + x[:, 1::2, 1::2])  # B, 64, 64, 3
+    n = S.shape[0] * S.shape[1] * S.shape[2]
+    s1 = S.sum(axis=(0, 1, 2)).astype(object)
+    s2 = (S * S).sum(axis=(0, 1, 2)).astype(object)
+    mean = np.array([float(s1[c]) / (4.0 * n) for c in range(3)], dtype=np.float32)
+    var = [float(n * s2[c] - s1[c] * s1[c]) / (16.0 * n * (n - 1)) for c in range(3)]
+    std = np.sqrt(np.array(var, dtype=np.float64)).astype(np.float32)
+    y = (S.astype(np.float32) * 0.25).transpose(0, 3, 1, 2)
+    assert np.array_equal(y, O.bilinear_resize(x, 64, 64, layout=O.NHWC))  # the box identity itself
+    ref = O.normalize_per_channel(y, channel_means=mean.reshape(1, 3, 1, 1), channel_stds=std.reshape(1, 3, 1, 1), min_value=-3, max_value=3)
+    out = host(T.preprocess_tiles(dev(x), layout="nhwc", output_hw=(64, 64), min_value=-3, max_value=3))
+    assert np.array_equal(out, ref)
+    xp = np.ascontiguousarray(x.transpose(0, 3, 1, 2))
+    out = host(T.preprocess_tiles(dev(xp), layout="nchw", output_hw=(64, 64), min_value=-3, max_value=3, out_dtype=torch.bfloat16))
+    assert np.array_equal(out, O.bf16_round(ref))
 
 
 def test_low_variance_and_constant_tiles():
