@@ -54,14 +54,14 @@ struct KnnPlan {
 };
 
 // ncta = 2: CTA pairs (cta_group::2) — an M block is 256 queries and the schedulable units are SM pairs.
-KnnPlan plan_knn(long long n, int q, int sms_total, int ncta) {
+KnnPlan plan_knn(long long n, int q, int k, int sms_total, int ncta) {
   KnnPlan p;
   const int sms = std::max(1, sms_total / ncta);
   p.mb = (q + BM * ncta - 1) / (BM * ncta);
   p.nb = (n + BN - 1) / BN;
   if (p.nb < 1) p.nb = 1;
   const long long max_s = std::max<long long>(1, std::min<long long>(p.nb, 4096));
-  // fewest splits whose item count fills whole waves of `sms` CTAs to >= 97 %; else the best seen
+  // fewest splits whose item count fills whole waves of `sms` units to >= 99.5 %; else the best seen
   int best_s = 1;
   double best_eff = -1.0;
   for (long long s = 1; s <= max_s; ++s) {
@@ -72,7 +72,9 @@ KnnPlan plan_knn(long long n, int q, int sms_total, int ncta) {
     const bool long_enough = (p.nb / s) >= 16 || s == 1;
     if (!long_enough) break;
     if (eff > best_eff + 1e-9) { best_eff = eff; best_s = static_cast<int>(s); }
-    if (eff >= 0.97) break;
+    // every extra split costs a partial list per query (prune, write, merge): cheap for small k,
+    // noticeable for the 256-entry buffers of large k
+    if (eff >= (k <= kSmallK ? 0.995 : 0.97)) break;
   }
   p.splits = best_s;
   p.items = static_cast<long long>(p.mb) * p.splits;
@@ -697,7 +699,7 @@ size_t isx_knn_workspace_bytes(int64_t n, int q, int d, int k) {
   int sms = 148;
   if (device_sm_count(&sms) != ISX_OK) sms = 148;
   // cover either scheduling mode (the choice may be overridden at search time)
-  return std::max(knn_workspace(plan_knn(n, q, sms, 1), q, k).total, knn_workspace(plan_knn(n, q, sms, 2), q, k).total);
+  return std::max(knn_workspace(plan_knn(n, q, k, sms, 1), q, k).total, knn_workspace(plan_knn(n, q, k, sms, 2), q, k).total);
 }
 
 int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const void* queries,
@@ -723,7 +725,7 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
   int rc = device_sm_count(&sms);
   if (rc != ISX_OK) return rc;
   const int ncta = (sms >= 2) ? knn_ncta(q) : 1;
-  const KnnPlan plan = plan_knn(n, q, sms, ncta);
+  const KnnPlan plan = plan_knn(n, q, k, sms, ncta);
   const KnnWorkspace ws = knn_workspace(plan, q, k);
   ISX_REQUIRE(workspace != nullptr && workspace_bytes >= ws.total, "%s: workspace too small (%zu < %zu)", fn,
               workspace_bytes, ws.total);
