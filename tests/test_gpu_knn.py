@@ -189,3 +189,43 @@ def test_store_format_bridge_blobs_to_search():
     check(O.maps_to_rows(maps), O.bf16_round(maps[4, :, 2, 3].reshape(1, -1)), 3, scores, idx)
     with pytest.raises(ValueError):
         F.decode_embedding_blob(records[0][0], 72, 5, 5)
+
+
+def test_full_size_store_sampled_queries():
+    """BASELINE.json config 2 at full size (1 M x 1280 bf16 store, 10 k queries, k = 10): every
+    result row is ordered and in range; 64 sampled queries are checked against an fp32 torch brute
+    force over the full store (library code, test side only); merging 8 row shards reproduces the
+    unsharded answer (the size-independent property behind the multi-GPU path)."""
+    n, d, q, k = 1_000_000, 1280, 10_000, 10
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    store = torch.empty((n, d), dtype=torch.bfloat16, device="cuda")
+    for s in range(0, n, 1 << 18):
+        e = min(n, s + (1 << 18))
+        store[s:e] = torch.randn((e - s, d), generator=g, device="cuda").to(torch.bfloat16)
+    queries = torch.randn((q, d), generator=g, device="cuda").to(torch.bfloat16)
+    st = S.EmbeddingStore(store)
+    scores, idx = st.search(queries, k)
+    assert scores.shape == (q, k) and int(idx.min()) >= 0 and int(idx.max()) < n
+    assert torch.all(scores[:, 1:] <= scores[:, :-1])
+    pick = torch.arange(0, q, q // 64, device="cuda")[:64]
+    qn = torch.nn.functional.normalize(queries[pick].float(), dim=1)
+    best_v = torch.full((64, k), -2.0, device="cuda")
+    best_i = torch.zeros((64, k), dtype=torch.int64, device="cuda")
+    for s in range(0, n, 1 << 18):
+        e = min(n, s + (1 << 18))
+        sc = qn @ torch.nn.functional.normalize(store[s:e].float(), dim=1).T
+        v, i = sc.topk(k, dim=1)
+        cv, ci = torch.cat([best_v, v], 1), torch.cat([best_i, i + s], 1)
+        o = cv.argsort(dim=1, descending=True, stable=True)[:, :k]
+        best_v, best_i = cv.gather(1, o), ci.gather(1, o)
+    assert torch.allclose(scores[pick], best_v, atol=SCORE_TOL)
+    same = (idx[pick] == best_i).float().mean()
+    assert float(same) > 0.98  # differences only across score gaps below the tolerance
+    parts_s, parts_i = [], []
+    for r in range(8):
+        b, e = S.shard_range(n, 8, r)
+        ps, pi = S.EmbeddingStore(store[b:e], index_base=b).search_raw(queries, k)
+        parts_s.append(ps)
+        parts_i.append(pi)
+    ms, mi = S.merge_topk(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.equal(mi.to(torch.int64), idx) and torch.allclose(ms, scores, atol=1e-6)

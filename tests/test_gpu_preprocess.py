@@ -220,3 +220,47 @@ def test_errors_and_edge_cases():
     # round trip property at a larger size: resize to the same size is the identity cast
     x = torch.randint(0, 256, (2, 3, 50, 70), dtype=torch.uint8).cuda()
     assert torch.equal(T.resize(x, (50, 70)), x.float())
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json config 3 at full size (4096 tiles of 512x512x3), through size-independent
+    properties: the reference's own test property (per-channel mean 0 / std 1 of the normalised
+    batch, tests/test_image/test_transform.py:14-24), clip bounds, layout independence, the 2x box
+    identity, and a sampled bit-exact comparison with the oracle."""
+    B, H, W = 4096, 512, 512
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    tiles = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device="cuda", generator=g)
+    out = T.preprocess_tiles(tiles, layout="nhwc")  # no clip: statistics are exactly testable
+    assert out.shape == (B, 3, H, W) and out.dtype == torch.float32
+    m = out.mean(dim=(0, 2, 3), dtype=torch.float64)
+    s = out.double().std(dim=(0, 2, 3)) if False else torch.sqrt((out.double() ** 2).mean(dim=(0, 2, 3)) - m**2)
+    assert torch.all(m.abs() < 1e-4) and torch.all((s - 1).abs() < 1e-4)
+    # sampled tiles, bit-exact against the oracle given the batch statistics the kernel derived
+    x64 = tiles[:1].double()
+    xs = tiles.view(-1, 3)
+    n = xs.shape[0]
+    s1 = xs.sum(dim=0, dtype=torch.int64).cpu().numpy().astype(object)
+    s2 = (xs.to(torch.int64) ** 2).sum(dim=0).cpu().numpy().astype(object)
+    mean = np.array([float(s1[c]) / n for c in range(3)], dtype=np.float32)
+    std = np.sqrt(np.array([float(n * s2[c] - s1[c] * s1[c]) / (float(n) * (n - 1)) for c in range(3)])).astype(np.float32)
+    pick = [0, 1234, B - 1]
+    ref = O.normalize_per_channel(
+        np.ascontiguousarray(tiles[pick].cpu().numpy().transpose(0, 3, 1, 2)),
+        channel_means=mean.reshape(1, 3, 1, 1), channel_stds=std.reshape(1, 3, 1, 1), min_value=-3, max_value=3,
+    )
+    del out, x64
+    clipped = T.preprocess_tiles(tiles, layout="nhwc", min_value=-3, max_value=3)
+    assert float(clipped.min()) >= -3.0 and float(clipped.max()) <= 3.0
+    assert np.array_equal(host(clipped[pick]), ref)
+    # planar input gives the same bits
+    planar = tiles.permute(0, 3, 1, 2).contiguous()
+    assert torch.equal(T.preprocess_tiles(planar, min_value=-3, max_value=3), clipped)
+    del clipped
+    # max_side_length = 256: the resized batch is the 2x2 box mean, normalised with ITS statistics
+    small = T.preprocess_tiles(tiles, layout="nhwc", output_hw=(256, 256))
+    box = tiles.view(B, 256, 2, 256, 2, 3).float().sum(dim=(2, 4)).mul_(0.25).permute(0, 3, 1, 2)
+    bm = box.mean(dim=(0, 2, 3), dtype=torch.float64)
+    bs = torch.sqrt(((box.double() - bm.view(1, 3, 1, 1)) ** 2).sum(dim=(0, 2, 3)) / (box.numel() // 3 - 1))
+    expect = (box - bm.float().view(1, 3, 1, 1)) / (bs.float().view(1, 3, 1, 1) + 1e-6)
+    assert torch.equal(small, expect)
+    assert torch.equal(T.preprocess_tiles(planar, output_hw=(256, 256)), small)

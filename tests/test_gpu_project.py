@@ -134,3 +134,39 @@ def test_pipeline_predict_step_end_to_end(golden):
     scale = np.sqrt((ref.astype(np.float64) ** 2).mean())
     # the backbone is cuDNN on the GPU vs MKL on the CPU: allow its fp32 reordering on top
     assert np.all(np.abs(out - ref) <= 1e-3 * np.abs(ref) + 1e-3 * scale)
+
+
+def test_full_size_feature_map_properties():
+    """BASELINE.json config 3b at full size (4096 x 1280 x 16 x 16 fp32 -> 256-d): sampled images
+    against an fp64 torch evaluation of the reference's formula (embedding.py:74, data.py:118,
+    decomposition.py:91), layout of pipelines.py:82-84, and pooled == mean of normalised cells."""
+    import torch
+
+    from imagescry_b200.models.decomposition import PCA
+
+    B, E, h, w, k = 4096, 1280, 16, 16, 256
+    g = torch.Generator(device="cuda").manual_seed(7)
+    fmap = torch.empty((B, E, h, w), dtype=torch.float32, device="cuda")
+    for s in range(0, B, 256):
+        fmap[s:s + 256] = torch.randn((256, E, h, w), generator=g, device="cuda").abs_()
+    comps = torch.linalg.qr(torch.randn((E, k), generator=g, device="cuda"))[0]
+    pca = PCA(num_features=E, num_components=k).cuda()
+    pca.feature_means.data = torch.randn((1, E), generator=g, device="cuda") * 0.01
+    pca.component_vectors.data = comps.contiguous()
+    pca._fitted.data = torch.tensor(True, device="cuda")
+    pca._num_features.data = torch.tensor(E, device="cuda")
+    pca._num_components.data = torch.tensor(k, device="cuda")
+    out = pca.project_feature_map(fmap)
+    assert out.shape == (B, k, h, w) and out.stride() == (h * w * k, 1, w * k, k)  # NHWC memory
+    pooled = pca.project_feature_map(fmap, pool="mean")
+    assert pooled.shape == (B, k)
+    for b in (0, 777, B - 1):
+        x = fmap[b].double()
+        e = x / x.norm(dim=0, keepdim=True).clamp_min(1e-12)
+        flat = e.permute(1, 2, 0).reshape(-1, E)
+        ref = (flat - pca.feature_means.double()) @ pca.component_vectors.double()
+        got = out[b].permute(1, 2, 0).reshape(-1, k).double()
+        scale = ref.norm(dim=1, keepdim=True)
+        assert float(((got - ref).abs() / scale).max()) < 1e-4  # bar: 1e-3 relative
+        refp = (e.mean(dim=(1, 2)).unsqueeze(0) - pca.feature_means.double()) @ pca.component_vectors.double()
+        assert float((pooled[b].double() - refp[0]).abs().max() / refp.norm()) < 1e-4
