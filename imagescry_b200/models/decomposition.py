@@ -2,8 +2,8 @@
 
 `PCA.forward` / `PCA.transform` (`decomposition.py:79-91,150-165`) run the fused sm_100a projection
 kernel (`isx_l2norm_project` with `normalize=0`); `project_feature_map` exposes the fully fused
-L2-normalise (+pool) + projection of a backbone feature map.  `fit` (`:94-148`) is the reference's
-algorithm on torch (offline, not on the hot path — SURVEY.md §8f).
+L2-normalise (+pool) + projection of a backbone feature map.  `fit` (`:94-148`) takes its means
+and covariance from the sm_100a moment kernels (`isx_pca_moments`) for CUDA input.
 
 The reference derives from `LightningModule`; lightning is not part of this image, so the base is
 `torch.nn.Module` with the same hyper-parameter surface (`hparams`, `save_hyperparameters`).
@@ -164,23 +164,50 @@ class PCA(HParamsModule):
             _lib.check(rc, "isx_l2norm_project")
         return out.permute(0, 3, 1, 2) if pool is None else out
 
-    # ------------------------------------------------------------------ fit (offline)
+    # ------------------------------------------------------------------ fit
+    def _moments(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        """Feature means (F,) and covariance (F×F) of a CUDA matrix through `isx_pca_moments`."""
+        xf = x.float().contiguous()
+        n, F = xf.shape
+        lib = _lib.load()
+        mean = torch.empty(F, dtype=torch.float32, device=xf.device)
+        cov = torch.empty((F, F), dtype=torch.float32, device=xf.device)
+        ws_bytes = int(lib.isx_pca_moments_workspace_bytes(n, F))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xf.device)
+        rc = lib.isx_pca_moments(
+            xf.data_ptr(), n, F, mean.data_ptr(), cov.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(xf.device)
+        )
+        _lib.check(rc, "isx_pca_moments")
+        return mean, cov
+
     @jaxtyped(typechecker=typechecker)
     def fit(self, x: Float[Tensor, "num_samples num_features"]) -> "PCA":
-        """Fit by SVD of the centred data (`decomposition.py:94-148`): same component selection
-        rule (min/max components, minimum explained variance).  Runs on x's device with torch."""
+        """Fit (`decomposition.py:94-148`): same component-selection rule (min/max components,
+        minimum explained variance) and the same fitted tensors as the reference.
+
+        CUDA input: means and the F×F covariance come from the sm_100a moment kernels (one pass each
+        over x); its eigen-pairs are the reference's `vt` rows and `s²/(n-1)` (:122-125) without the
+        full SVD's n×n `U`.  Signs of the component vectors are as arbitrary as the reference's own.
+        CPU input (offline use, tests): the reference's algorithm on torch."""
         num_samples, num_features = x.shape
         if num_samples < 2:
             raise ValueError(f"num_samples must be at least 2, got {num_samples}")
         self._num_features = nn.Parameter(torch.tensor(num_features), requires_grad=False)
-        self.feature_means = nn.Parameter(x.mean(dim=0, keepdim=True), requires_grad=False)
-        x_centered = x - self.feature_means
-        # Only the singular values and right singular vectors are used; the reduced SVD yields the
-        # same `s` and `vt` as the reference's full one without the num_samples² `U`.
-        _, s, vt = torch.linalg.svd(x_centered, full_matrices=False)
-        if vt.shape[0] < num_features:  # fewer samples than features: pad like the full SVD's shapes
-            s = torch.cat([s, s.new_zeros(num_features - s.shape[0])])
-        eigenvalues = s**2 / (num_samples - 1)
+        if x.is_cuda:
+            mean, cov = self._moments(x)
+            self.feature_means = nn.Parameter(mean.reshape(1, -1), requires_grad=False)
+            evals, evecs = torch.linalg.eigh(cov.double())  # ascending; 6.5 MB problem at F = 1280
+            eigenvalues = evals.flip(0).clamp_min(0.0).float()
+            vt = evecs.flip(1).T.float()  # rows = principal directions, like the SVD's vt
+        else:
+            self.feature_means = nn.Parameter(x.mean(dim=0, keepdim=True), requires_grad=False)
+            x_centered = x - self.feature_means
+            # Only the singular values and right singular vectors are used; the reduced SVD yields
+            # the same `s` and `vt` as the reference's full one without the num_samples² `U`.
+            _, s, vt = torch.linalg.svd(x_centered, full_matrices=False)
+            if vt.shape[0] < num_features:  # fewer samples than features: pad like the full SVD's shapes
+                s = torch.cat([s, s.new_zeros(num_features - s.shape[0])])
+            eigenvalues = s**2 / (num_samples - 1)
         total_variance = torch.sum(eigenvalues)
         self.explained_variance = nn.Parameter(eigenvalues / total_variance, requires_grad=False)
         cumulative = torch.cumsum(self.explained_variance, dim=0)

@@ -112,6 +112,14 @@ int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, 
                        const void* packed, int k, float* out, void* workspace,
                        size_t workspace_bytes, isx_stream_t stream);
 
+/* ---- PCA.fit moments (models/decomposition.py:94-148) -------------------------------------------
+ * mean[F] = column means of x (n x F fp32, row-major; :116) and cov[F x F] = Xc^T Xc / (n - 1) with
+ * Xc = x - mean centred in fp32 as the reference does (:119).  The eigenvectors / eigenvalues of cov
+ * are the right singular vectors / s^2 / (n - 1) the reference takes from its SVD (:122-125). */
+size_t isx_pca_moments_workspace_bytes(int64_t n, int F);
+int isx_pca_moments(const float* x, int64_t n, int F, float* mean, float* cov, void* workspace,
+                    size_t workspace_bytes, isx_stream_t stream);
+
 /* ---- stage 3: exhaustive cosine k-NN -----------------------------------------------------------
  * No reference counterpart; semantics are the composition of the reference's
  * idioms: normalize(q) . normalize(e) with F.normalize's eps (embedding.py:74) and a stable

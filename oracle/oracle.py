@@ -386,3 +386,29 @@ def maps_to_rows(maps: np.ndarray, pool: str | None = None) -> np.ndarray:
     if pool == "mean":
         return bf16_round(maps.reshape(n, c, h * w).astype(np.float64).mean(axis=2).astype(np.float32))
     return bf16_round(flat_vectors(maps.astype(np.float32)))
+
+
+# ------------------------------------------------------------------------------------------------
+# PCA.fit (models/decomposition.py:94-148)
+# ------------------------------------------------------------------------------------------------
+def pca_fit(x: np.ndarray, *, min_num_components: int = 1, max_num_components: int | None = None,
+            min_explained_variance: float = 0.0):
+    """mean (:116) -> centre (:119) -> SVD (:122) -> eigenvalues s^2/(n-1) (:125) -> explained
+    variance ratio (:128) -> component count (:131-137) -> vt[:k].T (:140).
+    Returns (feature_means (1,F), component_vectors (F,k), explained_variance (F,), k).  Component
+    signs are whatever the SVD returns (the reference does not fix them either)."""
+    x = np.asarray(x, dtype=np.float32)
+    n, f = x.shape
+    means = x.mean(axis=0, keepdims=True, dtype=np.float32)
+    xc = x - means
+    _, s, vt = np.linalg.svd(xc.astype(np.float64), full_matrices=False)
+    if vt.shape[0] < f:
+        s = np.concatenate([s, np.zeros(f - s.shape[0])])
+    eig = s**2 / (n - 1)
+    explained = (eig / eig.sum()).astype(np.float32)
+    need = int(np.sum(np.cumsum(explained) < min_explained_variance) + 1)
+    k = max(min_num_components, need)
+    if max_num_components is not None:
+        k = min(max_num_components, k)
+    k = min(k, vt.shape[0])
+    return means, vt[:k].T.astype(np.float32), explained, k

@@ -170,3 +170,48 @@ def test_full_size_feature_map_properties():
         assert float(((got - ref).abs() / scale).max()) < 1e-4  # bar: 1e-3 relative
         refp = (e.mean(dim=(1, 2)).unsqueeze(0) - pca.feature_means.double()) @ pca.component_vectors.double()
         assert float((pooled[b].double() - refp[0]).abs().max() / refp.norm()) < 1e-4
+
+
+def test_pca_fit_gpu_moments_and_components(golden):
+    """PCA.fit on the GPU (isx_pca_moments + eigen-decomposition) vs the oracle's restatement of
+    decomposition.py:94-148: reference fixtures, then a larger correlated matrix.  Directions are
+    compared up to sign (the reference's SVD signs are arbitrary too); the projections then agree up
+    to those signs."""
+    import torch
+
+    from imagescry_b200.models.decomposition import PCA
+
+    g = golden("embed_pca")
+    for name in ("unc", "cor"):
+        x = g[f"pca_{name}_x"]
+        k_ref = int(g[f"pca_{name}_k"])
+        cum = np.cumsum(g[f"pca_{name}_explained"])
+        thr = float((cum[k_ref - 2] + cum[k_ref - 1]) / 2) if k_ref > 1 else float(cum[0] / 2)
+        pca = PCA(min_explained_variance=thr).cuda().fit(torch.from_numpy(x).cuda())
+        assert pca.num_components == k_ref
+        assert np.allclose(pca.feature_means.cpu().numpy(), g[f"pca_{name}_means"], atol=1e-6)
+        assert np.allclose(pca.explained_variance.cpu().numpy(), g[f"pca_{name}_explained"], atol=1e-5)
+        dots = np.abs(np.sum(pca.component_vectors.cpu().numpy() * g[f"pca_{name}_comps"], axis=0))
+        assert np.all(dots > 1 - 1e-4)
+        out = pca.transform(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.allclose(np.abs(out), np.abs(g[f"pca_{name}_out"]), atol=2e-4)
+
+    rng = np.random.default_rng(42)
+    n, F, r = 20000, 200, 12
+    basis = rng.standard_normal((r, F)).astype(np.float32)
+    x = (rng.standard_normal((n, r)).astype(np.float32) * np.linspace(10, 1, r, dtype=np.float32)) @ basis
+    x += 0.05 * rng.standard_normal((n, F)).astype(np.float32) + 3.0
+    means, comps, explained, k = O.pca_fit(x, min_explained_variance=0.99, max_num_components=64)
+    pca = PCA(min_explained_variance=0.99, max_num_components=64).cuda().fit(torch.from_numpy(x).cuda())
+    assert pca.num_components == k
+    assert np.allclose(pca.feature_means.cpu().numpy(), means, atol=1e-5)
+    assert np.allclose(pca.explained_variance.cpu().numpy(), explained, atol=1e-5)
+    got = pca.component_vectors.cpu().numpy()
+    assert np.all(np.abs(np.sum(got[:, :r] * comps[:, :r], axis=0)) > 1 - 1e-3)
+    # the moments themselves against fp64 numpy
+    mean_d, cov_d = pca._moments(torch.from_numpy(x).cuda())
+    ref_cov = np.cov(x.astype(np.float64), rowvar=False)
+    assert np.abs(cov_d.cpu().numpy() - ref_cov).max() <= 1e-5 * np.abs(ref_cov).max()
+    assert np.array_equal(cov_d.cpu().numpy(), cov_d.cpu().numpy().T)
+    with pytest.raises(ValueError):
+        PCA().cuda().fit(torch.zeros((1, 4)).cuda())

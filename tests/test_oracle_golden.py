@@ -225,3 +225,23 @@ def test_torch_port_matches_oracle(golden):
     s, i = TP.cosine_knn(torch.from_numpy(store), torch.from_numpy(q), 10, block=1024)
     rs, ri = O.cosine_knn(store, q, 10)
     assert np.array_equal(i.numpy(), ri) and np.allclose(s.numpy(), rs, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,mev", [("unc", None), ("cor", None)])
+def test_pca_fit_oracle_matches_reference_fit(golden, name, mev):
+    """oracle.pca_fit against the reference's own `PCA.fit` outputs on its test fixtures
+    (tests/test_models/test_decomposition.py:18-39 data; fixtures from oracle/make_golden.py)."""
+    g = golden("embed_pca")
+    x = g[f"pca_{name}_x"]
+    k_ref = int(g[f"pca_{name}_k"])
+    # the fixture was fitted with the min_explained_variance that yields k_ref components: recover it
+    expl = g[f"pca_{name}_explained"]
+    cum = np.cumsum(expl)
+    thr = float((cum[k_ref - 2] + cum[k_ref - 1]) / 2) if k_ref > 1 else float(cum[0] / 2)
+    means, comps, explained, k = O.pca_fit(x, min_explained_variance=thr)
+    assert k == k_ref
+    assert np.allclose(means, g[f"pca_{name}_means"], atol=1e-6)
+    assert np.allclose(explained, expl, atol=1e-5)
+    ref_c = g[f"pca_{name}_comps"]
+    dots = np.abs(np.sum(comps * ref_c, axis=0))  # same directions up to sign
+    assert np.all(dots > 1 - 1e-4)
