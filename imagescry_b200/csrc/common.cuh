@@ -339,6 +339,29 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc
       : "memory");
 }
 
+// A operand in tensor memory ("TS" form): D[tmem] (+)= A[tmem] * B[smem].  A is M x K with row m on
+// TMEM lane m and two consecutive 16-bit K elements per 32-bit column (K = 16 -> 8 columns).
+__device__ __forceinline__ void tc_mma_f16_pair_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                                   uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: 32 lanes x 8 consecutive 32-bit columns (one row per thread)
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major operand tile stored as rows of 128 bytes with the
 // 128-byte swizzle (exactly what a SWIZZLE_128B TMA box of 128-byte inner extent produces).
 // Eight rows form one 1024-byte swizzle atom; atoms are stacked along M/N (SBO = 1024 bytes).

@@ -533,6 +533,264 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
 }
 
 // ------------------------------------------------------------------------------------------
+// K3t: the per-cell kernel with the A operand in TENSOR MEMORY (CTA pairs only).
+// The converted bf16 hi/lo operand never touches shared memory: the transform warps write it with
+// tcgen05.st straight into TMEM columns next to the accumulator and the MMAs take A from there
+// (tcgen05.mma ... [d], [a_tmem], b_desc).  Per k-block that removes 32 KB of shared-memory stores,
+// 48 KB of operand reads and the generic->async proxy fence from the one 128 B/clk shared-memory
+// port, and frees 64 KB for a deeper raw ring (4 x 32 KB in flight per SM).
+//   TMEM columns: [0, 256) accumulator (single stage: the epilogue of tile t runs before the MMAs of
+//   tile t + 1; the transform of t + 1 overlaps it), [256, 256 + 64 s) A stages (hi 32 | lo 32 cols).
+//   warp 0 weight TMA (half of the rows per CTA), warp 1 MMA issuer (leader), warp 2 TMEM alloc,
+//   warp 3 raw-tile TMA, warps 4-7 epilogue, warps 8-23 transform: warp tw owns TMEM lane quarter
+//   tw % 4 (rows = cells 32 (tw % 4) + lane) and features 16 (tw / 4) .. + 15 of every k-block.
+// ------------------------------------------------------------------------------------------
+struct ProjTSmem {
+  static constexpr int A_STAGES = 3, W_STAGES = 2, RAW_STAGES = 4;
+  static constexpr uint32_t W_PART_BYTES = (kMaxComponents / 2) * PK * 2;  // 16 KB
+  static constexpr uint32_t W_STAGE_BYTES = 2 * W_PART_BYTES;              // hi + lo
+  static constexpr uint32_t RAW_STAGE_BYTES = PM * PK * 4;                 // 32 KB
+  static constexpr uint32_t kWOff = 0;
+  static constexpr uint32_t kRawOff = kWOff + W_STAGES * W_STAGE_BYTES;
+  static constexpr uint32_t kSsOff = kRawOff + RAW_STAGES * RAW_STAGE_BYTES;  // [2][4 feature groups][128 rows]
+  static constexpr uint32_t kBarOff = kSsOff + 2 * 4 * PM * 4;
+  static constexpr uint32_t kNumBars = 2 * A_STAGES + 2 * W_STAGES + 2 * RAW_STAGES + 2 + 4;
+  static constexpr uint32_t kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr uint32_t kTotal = kTmemPtrOff + 16;
+  static constexpr uint32_t kDynamicBytes = kTotal + 1024;
+  static constexpr uint32_t kAColumn0 = kMaxComponents;  // first A column in TMEM
+};
+constexpr int kProjTThreads = (kTransformWarp0 + 16) * 32;
+
+__global__ void __launch_bounds__(kProjTThreads, 1)
+l2norm_project_tmem_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_constant__ CUtensorMap tmap_wlo,
+                           const __grid_constant__ CUtensorMap tmap_x, const ProjParams p) {
+  using L = ProjTSmem;
+  constexpr int A_STAGES = L::A_STAGES, W_STAGES = L::W_STAGES, RAW_STAGES = L::RAW_STAGES;
+  const uint32_t rank = cluster_ctarank();
+  const long long unit = blockIdx.x / 2, num_units = gridDim.x / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* a_full = bars;                       // [A]   16 transform warps x 2 CTAs (on the leader)
+  uint64_t* a_empty = a_full + A_STAGES;         // [A]   tcgen05.commit (both CTAs)
+  uint64_t* w_full = a_empty + A_STAGES;         // [W]   TMA of both CTAs (on the leader)
+  uint64_t* w_empty = w_full + W_STAGES;         // [W]   tcgen05.commit (both CTAs)
+  uint64_t* raw_full = w_empty + W_STAGES;       // [RAW] TMA
+  uint64_t* raw_empty = raw_full + RAW_STAGES;   // [RAW] 16 transform warps
+  uint64_t* tmem_full = raw_empty + RAW_STAGES;  // accumulator complete (both CTAs)
+  uint64_t* tmem_empty = tmem_full + 1;          // 4 epilogue warps x 2 CTAs (on the leader)
+  uint64_t* ss_full = tmem_empty + 1;            // [2]   16 transform warps
+  uint64_t* ss_empty = ss_full + 2;              // [2]   4 epilogue warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
+  float* ss_s = reinterpret_cast<float*>(smem + L::kSsOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.E + PK - 1) / PK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_whi);
+    prefetch_tmap(&tmap_wlo);
+    prefetch_tmap(&tmap_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 16 * 2); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&w_full[i], 2); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 16); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4 * 2);
+    for (int i = 0; i < 2; ++i) { mbar_init(&ss_full[i], 16); mbar_init(&ss_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int w_rows = p.k_pad / 2;
+  const uint32_t w_part_bytes = static_cast<uint32_t>(w_rows) * PK * 2;
+  const long long my_tiles = (p.tiles - unit + num_units - 1) / num_units;
+  const long long total_seq = my_tiles * num_kb;
+
+  if (warp == 0) {
+    // ===================== weight TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const int32_t row0 = static_cast<int32_t>(rank) * w_rows;
+      for (long long seq = 0; seq < total_seq; ++seq) {
+        const int kb = static_cast<int>(seq % num_kb);
+        mbar_wait(&w_empty[stage], phase ^ 1);
+        uint8_t* dst = smem + L::kWOff + stage * L::W_STAGE_BYTES;
+        mbar_arrive_expect_tx_leader(&w_full[stage], 2 * w_part_bytes);
+        tma_load_2d_pair(dst, &tmap_whi, &w_full[stage], kb * PK, row0, kEvictLast);
+        tma_load_2d_pair(dst + L::W_PART_BYTES, &tmap_wlo, &w_full[stage], kb * PK, row0, kEvictLast);
+        if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(/*bf16*/ 1, PM * 2, static_cast<uint32_t>(p.k_pad));
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, tph = 0;
+      for (long long tile = 0; tile < my_tiles; ++tile) {
+        mbar_wait(tmem_empty, tph ^ 1);  // the epilogues of both CTAs drained the accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&w_full[ws], wph);
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t a_hi = tmem_base + L::kAColumn0 + as * 64;
+          const uint32_t a_lo = a_hi + 32;
+          const uint32_t w_hi = smem_u32(smem + L::kWOff + ws * L::W_STAGE_BYTES);
+          const uint32_t w_lo = w_hi + L::W_PART_BYTES;
+#pragma unroll
+          for (int k = 0; k < PK / P_UMMA_K; ++k) {
+            const uint64_t dwh = make_kmajor_sw128_desc(w_hi + k * P_UMMA_K * 2);
+            const uint64_t dwl = make_kmajor_sw128_desc(w_lo + k * P_UMMA_K * 2);
+            tc_mma_f16_pair_ts(tmem_base, a_hi + k * 8, dwh, idesc, (kb | k) != 0);
+            tc_mma_f16_pair_ts(tmem_base, a_lo + k * 8, dwh, idesc, 1);
+            tc_mma_f16_pair_ts(tmem_base, a_hi + k * 8, dwl, idesc, 1);
+          }
+          tc_commit_pair(&a_empty[as]);
+          tc_commit_pair(&w_empty[ws]);
+          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+        }
+        tc_commit_pair(tmem_full);
+        tph ^= 1;
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== raw-tile TMA producer =====================
+    if (lane == 0) {
+      uint32_t rs = 0, rph = 0;
+      for (long long tile = unit; tile < p.tiles; tile += num_units) {
+        const long long R0 = (tile * 2 + rank) * PM;
+        const long long img = R0 / p.hw;
+        const int cell = static_cast<int>(R0 - img * p.hw);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&raw_empty[rs], rph ^ 1);
+          mbar_arrive_expect_tx(&raw_full[rs], L::RAW_STAGE_BYTES);
+          tma_load_3d(smem + L::kRawOff + rs * L::RAW_STAGE_BYTES, &tmap_x, &raw_full[rs], cell, kb * PK,
+                      static_cast<int32_t>(img), kEvictFirst);
+          if (++rs == RAW_STAGES) { rs = 0; rph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= kTransformWarp0) {
+    // ===================== transform: raw fp32 (smem) -> bf16 hi/lo (TMEM) =====================
+    const int tw = warp - kTransformWarp0;
+    const int lq = tw & 3;            // == warp % 4: the TMEM lane quarter this warp may access
+    const int fg = tw >> 2;           // feature group: 16 features of the k-block
+    const int m = lq * 32 + lane;     // row (cell) inside the tile
+    const int cb = min(p.hw, PM);     // raw box layout: [image][feature][cell], cb cells per image row
+    const int m_off = (m / cb) * (PK * cb) + (m % cb) + fg * 16 * cb;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + L::kAColumn0 + fg * 8;
+    float ss = 0.f;
+    uint32_t as = 0, aph = 0, rs = 0, rph = 0, sst = 0, ssph = 0;
+    int pr_kb = 0;
+    for (long long seq = 0; seq < total_seq; ++seq) {
+      mbar_wait(&raw_full[rs], rph);
+      const float* raw = reinterpret_cast<const float*>(smem + L::kRawOff + rs * L::RAW_STAGE_BYTES) + m_off;
+      float x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = raw[i * cb];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[rs]);  // release: this warp's reads of the stage are done
+      if (++rs == RAW_STAGES) { rs = 0; rph ^= 1; }
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a = x[2 * i], b = x[2 * i + 1];
+        ss = fmaf(a, a, ss);
+        ss = fmaf(b, b, ss);
+        // hi = x truncated to bf16 (a mask); lo = RN_bf16(x - hi): |x - hi - lo| <= 2^-16 |x|
+        const uint32_t ab = __float_as_uint(a), bb = __float_as_uint(b);
+        hi[i] = __byte_perm(ab, bb, 0x7632);
+        const float la = a - __uint_as_float(ab & 0xFFFF0000u);
+        const float lb = b - __uint_as_float(bb & 0xFFFF0000u);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(la, lb);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      mbar_wait(&a_empty[as], aph ^ 1);
+      tc_fence_after();
+      tmem_st_32x8(t_row + as * 64, hi);
+      tmem_st_32x8(t_row + as * 64 + 32, lo);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&a_full[as]);
+      if (++as == A_STAGES) { as = 0; aph ^= 1; }
+      if (++pr_kb == num_kb) {
+        // last k-block of the tile: publish this warp's share of the rows' sums of squares
+        pr_kb = 0;
+        mbar_wait(&ss_empty[sst], ssph ^ 1);
+        ss_s[(sst * 4 + fg) * PM + m] = ss;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ss_full[sst]);
+        ss = 0.f;
+        if (++sst == 2) { sst = 0; ssph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter
+    const int row = ew * 32 + lane;
+    uint32_t sst = 0, ssph = 0, tph = 0;
+    const bool vec_ok = (p.k & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0;
+    for (long long tile = unit; tile < p.tiles; tile += num_units) {
+      const long long R = (tile * 2 + rank) * PM + row;
+      mbar_wait(&ss_full[sst], ssph);
+      float rn = 1.0f;
+      if (p.normalize) {
+        const float* sp = ss_s + sst * 4 * PM + row;
+        const float ssum = (sp[0] + sp[PM]) + (sp[2 * PM] + sp[3 * PM]);
+        rn = 1.0f / fmaxf(sqrtf(ssum), 1e-12f);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ss_empty[sst]);
+      if (++sst == 2) { sst = 0; ssph ^= 1; }
+      mbar_wait(tmem_full, tph);
+      tph ^= 1;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+      float* orow = p.out + R * p.k;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.k_pad; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(taddr + c0, r);
+        tc_wait_ld();
+        if (R < p.m_total) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), rn, __ldg(p.bias + c0 + j));
+          if (vec_ok && c0 + 16 <= p.k) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(orow + c0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.k) orow[c0 + j] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tmem_empty);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K3p: pooled[b][e] = (1/hw) * sum_cells x[b][e][cell] * rnorm[b][cell]  — one pass over the map.
 // One CTA per image at a time; 16-cell slabs [E][16] double-buffered in shared memory via cp.async.
 // ------------------------------------------------------------------------------------------
@@ -816,8 +1074,31 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
     p.prefetch = 1;
   }
   if constexpr (NCTA == 2) {
-    static const bool staged_off = [] { const char* e = getenv("ISX_PROJECT_STAGED"); return e && e[0] == '0'; }();
-    if (p.prefetch && !staged_off) return launch_project_kernel<-1, 2>(twh, twl, tx, p, grid, stream);
+    // ISX_PROJECT_MODE = staged (default) | tmem | reg selects the per-cell kernel (A/B measurements,
+    // tests): staged = bf16 operand tiles in shared memory, tmem = A operand in tensor memory,
+    // reg = register-path loads without raw staging.  Read per call (a getenv, not on any hot loop).
+    const char* mode_env = getenv("ISX_PROJECT_MODE");
+    const int mode = (mode_env && mode_env[0] == 't') ? 0 : (mode_env && mode_env[0] == 'r') ? 2 : 1;
+    if (p.prefetch && mode == 0) {
+      auto kern = l2norm_project_tmem_kernel;
+      const int smem = static_cast<int>(ProjTSmem::kDynamicBytes);
+      ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>(grid));
+      cfg.blockDim = dim3(kProjTThreads);
+      cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      ISX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, twh, twl, tx, p));
+      return ISX_OK;
+    }
+    if (p.prefetch && mode == 1) return launch_project_kernel<-1, 2>(twh, twl, tx, p, grid, stream);
   }
   if (E % PK == 0 && hw == 256) return launch_project_kernel<256, NCTA>(twh, twl, tx, p, grid, stream);
   if (E % PK == 0 && hw == 64) return launch_project_kernel<64, NCTA>(twh, twl, tx, p, grid, stream);

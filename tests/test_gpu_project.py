@@ -215,3 +215,34 @@ def test_pca_fit_gpu_moments_and_components(golden):
     assert np.array_equal(cov_d.cpu().numpy(), cov_d.cpu().numpy().T)
     with pytest.raises(ValueError):
         PCA().cuda().fit(torch.zeros((1, 4)).cuda())
+
+
+@pytest.mark.parametrize("mode", ["staged", "tmem", "reg"])
+def test_per_cell_kernel_variants_agree(mode, monkeypatch):
+    """The three per-cell kernels (operand tiles in shared memory / A operand in tensor memory /
+    register-path loads) are selected by ISX_PROJECT_MODE; each must meet the oracle."""
+    import torch
+
+    from imagescry_b200.models.decomposition import PCA
+
+    monkeypatch.setenv("ISX_PROJECT_MODE", mode)
+    rng = np.random.default_rng(3)
+    B, E, h, w, k = 9, 320, 16, 16, 96  # hw = 256: 128-cell tiles are half images; ragged last pair
+    fmap = np.abs(rng.standard_normal((B, E, h, w))).astype(np.float32)
+    comps = np.linalg.qr(rng.standard_normal((E, k)))[0].astype(np.float32)
+    means = (rng.standard_normal(E) * 0.01).astype(np.float32)
+    pca = PCA(num_features=E, num_components=k)
+    pca.feature_means.data = torch.from_numpy(means).reshape(1, -1)
+    pca.component_vectors.data = torch.from_numpy(comps)
+    pca._fitted.data = torch.tensor(True)
+    pca._num_features.data = torch.tensor(E)
+    pca._num_components.data = torch.tensor(k)
+    pca = pca.cuda()
+    out = pca.project_feature_map(torch.from_numpy(fmap).cuda()).cpu().numpy()
+    ref = O.pipeline_project(fmap, means, comps)
+    scale = np.linalg.norm(ref, axis=1, keepdims=True)
+    assert (np.abs(out - ref) / scale).max() < 2e-5
+    fm8 = fmap[:, :, :8, :8].copy()  # hw = 64: a tile spans two images
+    out8 = pca.project_feature_map(torch.from_numpy(fm8).cuda()).cpu().numpy()
+    ref8 = O.pipeline_project(fm8, means, comps)
+    assert (np.abs(out8 - ref8) / np.linalg.norm(ref8, axis=1, keepdims=True)).max() < 2e-5
