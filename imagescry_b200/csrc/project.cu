@@ -121,6 +121,8 @@ struct ProjParams {
   const float* fmap;
   long long m_total;  // B * hw cells (rows)
   int E, hw, k, k_pad;
+  int rowmajor;       // staged kernel: fmap is an n x E row-major matrix (hw == 1); tmap_x is a 2-D
+                      // map with 128B-swizzled boxes of 128 rows x 32 features
   int prefetch;       // 1: tmap_x describes fmap and warp 3 prefetches tiles into L2 ahead of the transform
   int normalize;
   long long tiles;
@@ -274,8 +276,15 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&raw_empty[rs], rph ^ 1);
             mbar_arrive_expect_tx(&raw_full[rs], L::RAW_STAGE_BYTES);
-            tma_load_3d(smem + L::kRawOff + rs * L::RAW_STAGE_BYTES, &tmap_x, &raw_full[rs], cell, kb * PK,
-                        static_cast<int32_t>(img), kEvictFirst);
+            uint8_t* dst = smem + L::kRawOff + rs * L::RAW_STAGE_BYTES;
+            if (p.rowmajor) {
+              // two 128-row x 32-feature boxes (128-byte rows, 128B swizzle) per k-block
+              tma_load_2d(dst, &tmap_x, &raw_full[rs], kb * PK, static_cast<int32_t>(R0), kEvictFirst);
+              tma_load_2d(dst + L::RAW_STAGE_BYTES / 2, &tmap_x, &raw_full[rs], kb * PK + 32, static_cast<int32_t>(R0),
+                          kEvictFirst);
+            } else {
+              tma_load_3d(dst, &tmap_x, &raw_full[rs], cell, kb * PK, static_cast<int32_t>(img), kEvictFirst);
+            }
             if (++rs == static_cast<uint32_t>(RAW_STAGES)) { rs = 0; rph ^= 1; }
           }
         }
@@ -320,10 +329,21 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
       int pr_kb = 0;
       for (long long seq = 0; seq < total_seq; ++seq) {
         mbar_wait(&raw_full[rs], rph);
-        const float* raw = reinterpret_cast<const float*>(smem + L::kRawOff + rs * L::RAW_STAGE_BYTES) + m_off;
         float x[16];
+        if (p.rowmajor) {
+          // [2 sub-boxes][128 rows][32 features], 16-byte chunks XOR-swizzled by row % 8
+          const uint8_t* rawb = smem + L::kRawOff + rs * L::RAW_STAGE_BYTES + (quarter >> 1) * (L::RAW_STAGE_BYTES / 2) + m * 128;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = raw[i * cb];
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = ((quarter & 1) * 4 + j) ^ (m & 7);
+            const float4 v = *reinterpret_cast<const float4*>(rawb + chunk * 16);
+            x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+          }
+        } else {
+          const float* raw = reinterpret_cast<const float*>(smem + L::kRawOff + rs * L::RAW_STAGE_BYTES) + m_off;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = raw[i * cb];
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[rs]);  // release: this warp's reads of the stage are done
         if (++rs == static_cast<uint32_t>(RAW_STAGES)) { rs = 0; rph ^= 1; }
@@ -1063,6 +1083,17 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
   // whole number of images (128 % hw == 0); other shapes run without the prefetcher
   CUtensorMap tx = twh;
   p.prefetch = 0;
+  p.rowmajor = 0;
+  if constexpr (NCTA == 2) {
+    // n x E row-major input (PCA.transform's flat vectors, the pooled rows): 2-D map, swizzled boxes
+    if (hw == 1 && E % 4 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15u) == 0 && m_total < (1ll << 31)) {
+      rc = encode_tmap_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, fmap, static_cast<uint64_t>(m_total),
+                          static_cast<uint64_t>(E), static_cast<uint64_t>(E) * 4, PM, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != ISX_OK) return rc;
+      p.rowmajor = 1;
+      return launch_project_kernel<-1, 2>(twh, twl, tx, p, grid, stream);
+    }
+  }
   const long long images = m_total / hw;
   if (hw % 4 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15u) == 0 && (hw % PM == 0 || PM % hw == 0) && images >= 1) {
     const uint32_t cells_box = static_cast<uint32_t>(std::min(hw, PM));
