@@ -430,55 +430,59 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / CHUNK; ++chunk) {
-          uint32_t r[CHUNK];
-          if (CHUNK == 32) tmem_ld_32x32(taddr + chunk * CHUNK, reinterpret_cast<uint32_t(&)[32]>(r));
-          else tmem_ld_32x16(taddr + chunk * CHUNK, reinterpret_cast<uint32_t(&)[16]>(r));
+        for (int ld = 0; ld < BN / 32; ++ld) {
+          // one 32-column TMEM load (one wait) feeds 32 / CHUNK selection windows
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ld * 32, r);
           tc_wait_ld();
-          const float4* rn4 = reinterpret_cast<const float4*>(rn + chunk * CHUNK);
-          float vmax = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < CHUNK / 4; ++j) {
-            const float4 w = rn4[j];
-            const float a = __uint_as_float(r[4 * j + 0]) * w.x;
-            const float b = __uint_as_float(r[4 * j + 1]) * w.y;
-            const float c = __uint_as_float(r[4 * j + 2]) * w.z;
-            const float d = __uint_as_float(r[4 * j + 3]) * w.w;
-            r[4 * j + 0] = __float_as_uint(a);
-            r[4 * j + 1] = __float_as_uint(b);
-            r[4 * j + 2] = __float_as_uint(c);
-            r[4 * j + 3] = __float_as_uint(d);
-            vmax = fmaxf(vmax, fmaxf(fmaxf(a, b), fmaxf(c, d)));
-          }
-          if (vmax > thr) {
-            // rare path: some score in this chunk beats the row's threshold
-            const int cbase = chunk * CHUNK;
+          for (int h = 0; h < 32 / CHUNK; ++h) {
+            const int cbase = ld * 32 + h * CHUNK;
+            const float4* rn4 = reinterpret_cast<const float4*>(rn + cbase);
+            float vmax = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-              const float v = __uint_as_float(r[j]);
-              if (v > thr && cbase + j < ncols) {
-                my_buf[cnt ^ my_swz] = make_uint2(r[j], static_cast<uint32_t>(n0 + cbase + j));
-                ++cnt;
+            for (int j = 0; j < CHUNK / 4; ++j) {
+              const float4 w = rn4[j];
+              const int o = h * CHUNK + 4 * j;
+              const float a = __uint_as_float(r[o + 0]) * w.x;
+              const float b = __uint_as_float(r[o + 1]) * w.y;
+              const float c = __uint_as_float(r[o + 2]) * w.z;
+              const float d = __uint_as_float(r[o + 3]) * w.w;
+              r[o + 0] = __float_as_uint(a);
+              r[o + 1] = __float_as_uint(b);
+              r[o + 2] = __float_as_uint(c);
+              r[o + 3] = __float_as_uint(d);
+              vmax = fmaxf(vmax, fmaxf(fmaxf(a, b), fmaxf(c, d)));
+            }
+            if (vmax > thr) {
+              // rare path: some score in this window beats the row's threshold
+#pragma unroll
+              for (int j = 0; j < CHUNK; ++j) {
+                const float v = __uint_as_float(r[h * CHUNK + j]);
+                if (v > thr && cbase + j < ncols) {
+                  my_buf[cnt ^ my_swz] = make_uint2(r[h * CHUNK + j], static_cast<uint32_t>(n0 + cbase + j));
+                  ++cnt;
+                }
               }
             }
-          }
-          // warp-uniform: prune every row that could overflow during the next chunk
-          uint32_t need = __ballot_sync(kFullMask, cnt > CAP - CHUNK);
-          while (need) {
-            const int rr = __ffs(need) - 1;
-            need &= need - 1;
-            __syncwarp();
-            const int c = __shfl_sync(kFullMask, cnt, rr);
-            float nthr;
-            int ncnt;
-            prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr,
-                           ncnt, s_reg, i_reg);
-            __syncwarp();
-            if (lane == rr) {
-              cnt = ncnt;
-              if (nthr > thr) {
-                thr = nthr;
-                atomicMax(p.thr_shared + qrow, thr_encode(nthr));
+            // warp-uniform: prune every row that could overflow during the next window
+            uint32_t need = __ballot_sync(kFullMask, cnt > CAP - CHUNK);
+            while (need) {
+              const int rr = __ffs(need) - 1;
+              need &= need - 1;
+              __syncwarp();
+              const int c = __shfl_sync(kFullMask, cnt, rr);
+              float nthr;
+              int ncnt;
+              prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr,
+                             ncnt, s_reg, i_reg);
+              __syncwarp();
+              if (lane == rr) {
+                cnt = ncnt;
+                if (nthr > thr) {
+                  thr = nthr;
+                  atomicMax(p.thr_shared + qrow, thr_encode(nthr));
+                }
               }
             }
           }
