@@ -367,7 +367,7 @@ def run_b200(args) -> None:
     import torch.distributed as dist
 
     from imagescry_b200 import _lib
-    from imagescry_b200.search import EmbeddingStore, gather_partials, merge_topk, row_rnorm, shard_range
+    from imagescry_b200.search import EmbeddingStore, ShardedEmbeddingStore, gather_partials, merge_topk, row_rnorm, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -381,6 +381,9 @@ def run_b200(args) -> None:
     dev = torch.device("cuda", local_rank)
     dist_on = world > 1
     if dist_on:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     peaks = load_peaks()
@@ -463,12 +466,17 @@ def run_b200(args) -> None:
     out_i_host = torch.empty((Q, K), dtype=torch.int64).pin_memory()
     q_stage = torch.empty_like(queries)
 
+    sharded = ShardedEmbeddingStore.__new__(ShardedEmbeddingStore) if dist_on else None
+    if dist_on:
+        sharded.group, sharded.world_size, sharded.rank, sharded.local = None, world, rank, store
+
     def e2e_step():
-        q_stage.copy_(q_host, non_blocking=True)
         if dist_on:
-            s, i = step(q_stage, record=False)
+            # every rank uploads 1/N of the query rows; one all-gather over NVLink replicates them
+            s, i = step(sharded.replicate_queries(q_host), record=False)
             i = i.to(torch.int64)
         else:
+            q_stage.copy_(q_host, non_blocking=True)
             s, i = store.search(q_stage, K)
         out_s_host.copy_(s, non_blocking=True)
         out_i_host.copy_(i, non_blocking=True)
@@ -478,7 +486,8 @@ def run_b200(args) -> None:
     e2e = {
         "value": Q / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": q_host.numel() * 2,
         "d2h_bytes_per_step": out_s_host.numel() * 4 + out_i_host.numel() * 8, "ms_per_step": sec_e2e * 1e3,
-        "api": "EmbeddingStore.search(queries, k) on a device-resident store; queries from pinned host memory",
+        "api": ("ShardedEmbeddingStore: each rank uploads 1/N of the pinned host queries, all-gather over NVLink, local search, all-gather + merge"
+                if dist_on else "EmbeddingStore.search(queries, k) on a device-resident store; queries from pinned host memory"),
     }
 
     extra: dict = {}

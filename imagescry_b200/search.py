@@ -185,3 +185,23 @@ class ShardedEmbeddingStore:
         all_s, all_i = gather_partials(scores, idx, self.group)
         s, i = merge_topk(all_s, all_i, k)
         return s, i.to(torch.int64)
+
+    def replicate_queries(self, host_queries: Tensor) -> Tensor:
+        """Replicated device copy of a (pinned) host query matrix without sending it over PCIe once
+        per GPU: every rank uploads only its 1/G slice of the rows and one all-gather over NVLink
+        completes the copy.  All ranks must pass the same `host_queries`; the returned tensor is a
+        view of a staging buffer that the next call overwrites."""
+        import torch.distributed as dist
+
+        q, d = host_queries.shape
+        per = (q + self.world_size - 1) // self.world_size
+        dev = self.local.device
+        staging = getattr(self, "_q_staging", None)
+        if staging is None or staging.shape != (per * self.world_size, d) or staging.dtype != host_queries.dtype:
+            staging = torch.empty((per * self.world_size, d), dtype=host_queries.dtype, device=dev)
+            self._q_staging = staging
+        b, e = min(q, self.rank * per), min(q, (self.rank + 1) * per)
+        mine = staging[self.rank * per:self.rank * per + (e - b)]
+        mine.copy_(host_queries[b:e], non_blocking=True)
+        dist.all_gather_into_tensor(staging, staging[self.rank * per:(self.rank + 1) * per], group=self.group)
+        return staging[:q]
