@@ -61,9 +61,13 @@ KnnPlan plan_knn(long long n, int q, int k, int sms_total, int ncta) {
   p.nb = (n + BN - 1) / BN;
   if (p.nb < 1) p.nb = 1;
   const long long max_s = std::max<long long>(1, std::min<long long>(p.nb, 4096));
-  // fewest splits whose item count fills whole waves of `sms` units to >= 99.5 %; else the best seen
+  // Fewest splits whose item count fills whole waves of `sms` units to >= 97 %.  For small k the
+  // search goes on to >= 99.5 % as long as items stay long (>= 64 tiles): every extra split costs a
+  // partial list per query (final prune, write, merge) — cheap next to a long item, noticeable for
+  // short ones and for the 256-entry buffers of large k.
   int best_s = 1;
   double best_eff = -1.0;
+  bool have97 = false;
   for (long long s = 1; s <= max_s; ++s) {
     const long long items = static_cast<long long>(p.mb) * s;
     const long long waves = (items + sms - 1) / sms;
@@ -71,10 +75,10 @@ KnnPlan plan_knn(long long n, int q, int k, int sms_total, int ncta) {
     // keep items long enough to amortise the cold start of the running threshold
     const bool long_enough = (p.nb / s) >= 16 || s == 1;
     if (!long_enough) break;
+    if (have97 && (k > kSmallK || (p.nb / s) < 64)) break;
     if (eff > best_eff + 1e-9) { best_eff = eff; best_s = static_cast<int>(s); }
-    // every extra split costs a partial list per query (prune, write, merge): cheap for small k,
-    // noticeable for the 256-entry buffers of large k
-    if (eff >= (k <= kSmallK ? 0.995 : 0.97)) break;
+    if (eff >= 0.97) have97 = true;
+    if (eff >= 0.995) break;
   }
   p.splits = best_s;
   p.items = static_cast<long long>(p.mb) * p.splits;
