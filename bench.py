@@ -362,6 +362,73 @@ def bench_project(peaks: dict, steps: int, warmup: int) -> dict:
     return out
 
 
+def bench_sift_small(steps: int = 1) -> dict:
+    """BASELINE.json config 5 scaled to one GPU and 8192 tiles: HWC uint8 256x256 tiles -> stage 1 ->
+    EfficientNetV2-S features (torchvision module, NOT owned: reported only) -> L2 + mean pool + PCA
+    projection to 256-d (PCA fitted on the GPU from the first batch's cells) -> bf16 store ->
+    all-pairs k=10 graph.  Per-stage device times (CUDA events)."""
+    import torch
+
+    from imagescry_b200.models.decomposition import PCA
+    from imagescry_b200.models.embedding import EfficientNetEmbedder
+    from imagescry_b200.search import EmbeddingStore
+
+    n_tiles, bs, k_comp = 8192, 512, 256
+    torch.manual_seed(1234)
+    model = EfficientNetEmbedder(backbone_size="s").cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    tiles = torch.randint(0, 256, (n_tiles, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    t_pre = t_bb = t_proj = 0.0
+    pca = None
+    rows = []
+    with torch.inference_mode():
+        for s0 in range(0, n_tiles, bs):
+            batch = tiles[s0:s0 + bs]
+            e0 = ev()
+            x = model.preprocess_hwc(batch)
+            e1 = ev()
+            fmap = model(x)
+            e2 = ev()
+            if pca is None:
+                # fit on the L2-normalised cells of the first batch (reference: PCA.fit on flat vectors)
+                cells = torch.nn.functional.normalize(fmap, p=2, dim=1).permute(0, 2, 3, 1).reshape(-1, fmap.shape[1])
+                pca = PCA(min_num_components=k_comp, max_num_components=k_comp).cuda().fit(cells)
+                pca.packed_weights()
+                e2 = ev()
+            rows.append(pca.project_feature_map(fmap, pool="mean"))
+            e3 = ev()
+            torch.cuda.synchronize()
+            if s0 > 0:  # first batch = warm-up (cuDNN autotune, PCA fit)
+                t_pre += e0.elapsed_time(e1)
+                t_bb += e1.elapsed_time(e2)
+                t_proj += e2.elapsed_time(e3)
+        emb = torch.cat(rows)
+        e0 = ev()
+        store = EmbeddingStore(emb)
+        scores, idx = store.search(emb, 11)  # k + 1: the first hit of every row is the row itself
+        e1 = ev()
+        torch.cuda.synchronize()
+        t_search = e0.elapsed_time(e1)
+    timed = n_tiles - bs
+    self_first = float((idx[:, 0] == torch.arange(n_tiles, device="cuda")).float().mean())
+    out = {
+        "workload": f"{n_tiles} uint8 256x256x3 HWC tiles, batch {bs}, EfficientNetV2-S weights=None seed 1234 (fp32), pooled PCA-256, all-pairs k=10",
+        "preprocess_tiles_per_s": timed / (t_pre / 1e3), "backbone_img_per_s_not_owned": timed / (t_bb / 1e3),
+        "pool_project_tiles_per_s": timed / (t_proj / 1e3), "graph_rows_per_s": n_tiles / (t_search / 1e3),
+        "ms": {"preprocess": t_pre, "backbone": t_bb, "pool_project": t_proj, "store_build_and_all_pairs": t_search},
+        "self_match_first": self_first,
+    }
+    del tiles, model, store
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
@@ -502,6 +569,10 @@ def run_b200(args) -> None:
                 extra["project"] = bench_project(peaks, max(3, min(args.steps, 5)), 3)
             except Exception as ex:
                 extra["project"] = {"error": repr(ex)}
+            try:
+                extra["sift_small"] = bench_sift_small()
+            except Exception as ex:
+                extra["sift_small"] = {"error": repr(ex)}
             try:
                 cpu_baseline = cpu_knn_sample(store.embeddings.cpu(), q_host, seconds_target=12.0)
             except Exception as ex:

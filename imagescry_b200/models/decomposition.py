@@ -92,7 +92,13 @@ class PCA(HParamsModule):
         the projection kernel's TMA descriptors read.  Rebuilt when the parameters change."""
         cv, fm = self.component_vectors, self.feature_means
         _lib.require_cuda(cv, "PCA parameters")
-        key = (cv.data_ptr(), fm.data_ptr(), cv._version, fm._version, tuple(cv.shape), tuple(cv.stride()), str(cv.device))
+        def version(t: Tensor) -> int:
+            try:
+                return t._version
+            except RuntimeError:  # inference tensors (fitted under torch.inference_mode) have no counter
+                return -1
+
+        key = (cv.data_ptr(), fm.data_ptr(), version(cv), version(fm), tuple(cv.shape), tuple(cv.stride()), str(cv.device))
         if self._packed is None or self._packed_key != key:
             lib = _lib.load()
             F, k = cv.shape

@@ -215,6 +215,12 @@ def test_pca_fit_gpu_moments_and_components(golden):
     assert np.array_equal(cov_d.cpu().numpy(), cov_d.cpu().numpy().T)
     with pytest.raises(ValueError):
         PCA().cuda().fit(torch.zeros((1, 4)).cuda())
+    # fitted and used under inference mode (what Lightning's predict loop runs in): the fitted tensors
+    # are inference tensors without a version counter
+    with torch.inference_mode():
+        p2 = PCA(min_num_components=8, max_num_components=8).cuda().fit(torch.from_numpy(x).cuda())
+        out = p2.transform(torch.from_numpy(x[:64]).cuda())
+    assert out.shape == (64, 8) and torch.isfinite(out).all()
 
 
 @pytest.mark.parametrize("mode", ["staged", "tmem", "reg"])
