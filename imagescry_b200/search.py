@@ -137,6 +137,37 @@ class EmbeddingStore:
         return scores, idx.to(torch.int64)
 
 
+def drop_self_matches(scores: Tensor, indices: Tensor, query_rows: Tensor, k: int) -> tuple[Tensor, Tensor]:
+    """From Q×(k+1) results whose queries are store rows `query_rows` (global indices), remove each
+    query's own row and keep the first k of the rest (order preserved).  If the row itself is not
+    among the k+1 hits (k+1 exact duplicates with lower indices), the last hit is dropped."""
+    q, k1 = indices.shape
+    if k1 != k + 1:
+        raise ValueError(f"expected k + 1 = {k + 1} columns, got {k1}")
+    is_self = indices == query_rows.to(indices.dtype).reshape(-1, 1)
+    # position of the column to drop: the self hit, else the last column
+    drop = torch.where(is_self.any(dim=1), is_self.to(torch.int8).argmax(dim=1), torch.full((q,), k, device=indices.device))
+    cols = torch.arange(k, device=indices.device).reshape(1, -1)
+    take = cols + (cols >= drop.reshape(-1, 1)).to(cols.dtype)
+    return scores.gather(1, take), indices.gather(1, take)
+
+
+def knn_graph(store: "EmbeddingStore", k: int, *, block: int = 131072) -> tuple[Tensor, Tensor]:
+    """All-pairs similarity graph over a store (BASELINE.json config 5): the k nearest other rows of
+    every row.  Queries are the store's own rows, searched in blocks with k + 1 and the self match
+    removed.  Returns (scores N×k fp32, indices N×k int64)."""
+    n = len(store)
+    out_s = torch.empty((n, k), dtype=torch.float32, device=store.device)
+    out_i = torch.empty((n, k), dtype=torch.int64, device=store.device)
+    for b in range(0, n, block):
+        e = min(n, b + block)
+        s, i = store.search_raw(store.embeddings[b:e], k + 1, query_rnorm=store.rnorm[b:e])
+        rows = torch.arange(b, e, device=store.device) + store.index_base
+        s, i = drop_self_matches(s, i.to(torch.int64), rows, k)
+        out_s[b:e], out_i[b:e] = s, i
+    return out_s, out_i
+
+
 def knn_search(embeddings: Tensor, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
     """One-shot convenience: build an `EmbeddingStore` and search it."""
     return EmbeddingStore(embeddings).search(queries, k)

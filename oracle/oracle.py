@@ -412,3 +412,16 @@ def pca_fit(x: np.ndarray, *, min_num_components: int = 1, max_num_components: i
         k = min(max_num_components, k)
     k = min(k, vt.shape[0])
     return means, vt[:k].T.astype(np.float32), explained, k
+
+
+def knn_graph(store: np.ndarray, k: int) -> tuple[np.ndarray, np.ndarray]:
+    """All-pairs similarity graph (BASELINE.json config 5; SURVEY.md §8c `exclude_self=True`): the k
+    best neighbours of every store row other than the row itself, (score desc, index asc)."""
+    s, i = cosine_knn(store, store, k + 1)
+    n = store.shape[0]
+    out_s = np.full((n, k), -np.inf, dtype=np.float32)
+    out_i = np.full((n, k), -1, dtype=np.int64)
+    for r in range(n):
+        keep = i[r] != r
+        out_s[r], out_i[r] = s[r][keep][:k], i[r][keep][:k]
+    return out_s, out_i

@@ -229,3 +229,15 @@ def test_full_size_store_sampled_queries():
         parts_i.append(pi)
     ms, mi = S.merge_topk(torch.stack(parts_s), torch.stack(parts_i))
     assert torch.equal(mi.to(torch.int64), idx) and torch.allclose(ms, scores, atol=1e-6)
+
+
+def test_knn_graph_excludes_self():
+    """All-pairs graph (config 5 shape, d = 256): k nearest OTHER rows of every row, duplicates kept."""
+    store, _ = make(3000, 1, 256, seed=11, dup=True)  # rows 3, 17 and n-1 are identical
+    st = S.EmbeddingStore(torch.from_numpy(store).cuda())
+    s, i = S.knn_graph(st, 5, block=1024)
+    rs, ri = O.knn_graph(store, 5)
+    assert np.abs(s.cpu().numpy() - rs).max() <= SCORE_TOL
+    assert (i.cpu().numpy() == ri).mean() > 0.995
+    assert not (i.cpu() == torch.arange(3000).reshape(-1, 1)).any()
+    assert i[3, :2].tolist() == [17, 2999] and i[17, :2].tolist() == [3, 2999]
