@@ -356,6 +356,14 @@ def bench_project(peaks: dict, steps: int, warmup: int) -> dict:
                 "bound": "tensor", "achieved": tf, "peak": peak_sus, "unit": "TFLOP/s", "frac": tf / peak_sus,
                 "note": "issued bf16 FLOPs (3 passes of 2*cells*1280*256) / sustained cuBLAS bf16 peak",
             }
+    # opt-in single-pass mode (precision="fp16"): HBM-bound instead of tensor-bound
+    sec = timed_steps(lambda: pca.project_feature_map(fmap, precision="fp16"), steps, warmup, False)
+    algo = fmap.numel() * 4 + B * h * w * k * 4
+    out["per_cell_fp16_single_pass"] = {
+        "cells_per_s": B * h * w / sec, "tiles_per_s": B / sec, "ms": sec * 1e3, "algorithmic_bytes": algo,
+        "roofline": {"bound": "hbm", "achieved": algo / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": algo / sec / 1e9 / peaks["hbm_gbs"]},
+        "note": "one fp16 tensor pass; ~1e-5 of a row's norm vs ~1e-6 for the default three-pass bf16 split",
+    }
     out["batch"] = f"feature map {B}x{E}x{h}x{w} fp32 -> {k}-d"
     del fmap
     torch.cuda.empty_cache()

@@ -51,6 +51,10 @@ SIGNATURES: dict[str, tuple] = {
         c_int,
         [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
+    "isx_l2norm_project_fp16": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
     "isx_pca_moments_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "isx_pca_moments": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "isx_row_rnorm_bf16": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),

@@ -27,6 +27,8 @@
 // which then go through the same projection kernel as an n x F matrix (normalize = 0).
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -77,7 +79,7 @@ struct ProjSmem {
 
 struct PackedLayout {
   int k_pad, f_pad;
-  size_t hi_off, lo_off, bias_off, total;
+  size_t hi_off, lo_off, bias_off, h_off, total;  // h: the weights once more, as plain fp16 (single-pass mode)
 };
 
 PackedLayout packed_layout(int F, int k) {
@@ -88,7 +90,8 @@ PackedLayout packed_layout(int F, int k) {
   l.hi_off = 0;
   l.lo_off = (mat + 255) / 256 * 256;
   l.bias_off = l.lo_off + (mat + 255) / 256 * 256;
-  l.total = l.bias_off + (static_cast<size_t>(l.k_pad) * 4 + 255) / 256 * 256;
+  l.h_off = l.bias_off + (static_cast<size_t>(l.k_pad) * 4 + 255) / 256 * 256;
+  l.total = l.h_off + (mat + 255) / 256 * 256;
   return l;
 }
 
@@ -96,7 +99,7 @@ PackedLayout packed_layout(int F, int k) {
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ means, const float* __restrict__ comps, int F, int k,
                     long long ld_f, long long ld_k, int k_pad, int f_pad, __nv_bfloat16* __restrict__ w_hi,
-                    __nv_bfloat16* __restrict__ w_lo, float* __restrict__ bias) {
+                    __nv_bfloat16* __restrict__ w_lo, __half* __restrict__ w_h, float* __restrict__ bias) {
   const int lane = threadIdx.x & 31;
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (j >= k_pad) return;
@@ -111,6 +114,7 @@ pack_weights_kernel(const float* __restrict__ means, const float* __restrict__ c
     const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
     w_hi[static_cast<size_t>(j) * f_pad + f] = hi;
     w_lo[static_cast<size_t>(j) * f_pad + f] = lo;
+    w_h[static_cast<size_t>(j) * f_pad + f] = __float2half_rn(w);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
@@ -121,6 +125,8 @@ struct ProjParams {
   const float* fmap;
   long long m_total;  // B * hw cells (rows)
   int E, hw, k, k_pad;
+  int fast;           // staged kernel: one fp16 tensor pass (operands rounded to fp16, saturating) instead of
+                      // the three-pass bf16 split; tmap_whi then describes the fp16 weight matrix
   int rowmajor;       // staged kernel: fmap is an n x E row-major matrix (hw == 1); tmap_x is a 2-D
                       // map with 128B-swizzled boxes of 128 rows x 32 features
   int prefetch;       // 1: tmap_x describes fmap and warp 3 prefetches tiles into L2 ahead of the transform
@@ -205,7 +211,11 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&w_empty[stage], phase ^ 1);
           uint8_t* dst = smem + L::kWOff + stage * W_STAGE_BYTES;
-          if (NCTA == 2) {
+          if (NCTA == 2 && STAGED && p.fast) {
+            // single fp16 pass: one weight matrix (tmap_whi describes the fp16 copy)
+            mbar_arrive_expect_tx_leader(&w_full[stage], w_part_bytes);
+            tma_load_2d_pair(dst, &tmap_whi, &w_full[stage], kb * PK, row0, kEvictLast);
+          } else if (NCTA == 2) {
             mbar_arrive_expect_tx_leader(&w_full[stage], 2 * w_part_bytes);
             tma_load_2d_pair(dst, &tmap_whi, &w_full[stage], kb * PK, row0, kEvictLast);
             tma_load_2d_pair(dst + W_PART_BYTES, &tmap_wlo, &w_full[stage], kb * PK, row0, kEvictLast);
@@ -222,6 +232,8 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
     // ===================== MMA issuer =====================
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = make_idesc(/*bf16*/ 1, PM * NCTA, static_cast<uint32_t>(p.k_pad));
+      const uint32_t idesc_f16 = make_idesc(/*f16*/ 0, PM * NCTA, static_cast<uint32_t>(p.k_pad));
+      (void)idesc_f16;
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, acc = 0, acc_phase = 0;
       for (long long tile = unit; tile < p.tiles; tile += num_units) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -240,7 +252,9 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
             const uint32_t o = k * P_UMMA_K * 2;
             const uint64_t dah = make_kmajor_sw128_desc(a_hi + o), dal = make_kmajor_sw128_desc(a_lo + o);
             const uint64_t dwh = make_kmajor_sw128_desc(w_hi + o), dwl = make_kmajor_sw128_desc(w_lo + o);
-            if (NCTA == 2) {
+            if (NCTA == 2 && STAGED && p.fast) {
+              tc_mma_f16_pair(d_tmem, dah, dwh, idesc_f16, (kb | k) != 0);
+            } else if (NCTA == 2) {
               tc_mma_f16_pair(d_tmem, dah, dwh, idesc, (kb | k) != 0);
               tc_mma_f16_pair(d_tmem, dal, dwh, idesc, 1);
               tc_mma_f16_pair(d_tmem, dah, dwl, idesc, 1);
@@ -348,18 +362,30 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
         if (lane == 0) mbar_arrive(&raw_empty[rs]);  // release: this warp's reads of the stage are done
         if (++rs == static_cast<uint32_t>(RAW_STAGES)) { rs = 0; rph ^= 1; }
         uint32_t hi[8], lo[8];
+        if (p.fast) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a = x[2 * i], b = x[2 * i + 1];
-          ss = fmaf(a, a, ss);
-          ss = fmaf(b, b, ss);
-          // hi = x truncated to bf16 (a mask); lo = RN_bf16(x - hi): |x - hi - lo| <= 2^-16 |x|
-          const uint32_t ab = __float_as_uint(a), bb = __float_as_uint(b);
-          hi[i] = __byte_perm(ab, bb, 0x7632);
-          const float la = a - __uint_as_float(ab & 0xFFFF0000u);
-          const float lb = b - __uint_as_float(bb & 0xFFFF0000u);
-          const __nv_bfloat162 l2 = __floats2bfloat162_rn(la, lb);
-          lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+          for (int i = 0; i < 8; ++i) {
+            const float a = x[2 * i], b = x[2 * i + 1];
+            ss = fmaf(a, a, ss);
+            ss = fmaf(b, b, ss);
+            // one fp16 operand (11-bit significand), saturating: lower half = a, upper half = b
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(b), "f"(a));
+            lo[i] = 0u;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a = x[2 * i], b = x[2 * i + 1];
+            ss = fmaf(a, a, ss);
+            ss = fmaf(b, b, ss);
+            // hi = x truncated to bf16 (a mask); lo = RN_bf16(x - hi): |x - hi - lo| <= 2^-16 |x|
+            const uint32_t ab = __float_as_uint(a), bb = __float_as_uint(b);
+            hi[i] = __byte_perm(ab, bb, 0x7632);
+            const float la = a - __uint_as_float(ab & 0xFFFF0000u);
+            const float lb = b - __uint_as_float(bb & 0xFFFF0000u);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(la, lb);
+            lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
         }
         mbar_wait(&a_empty[stage], phase ^ 1);
         uint8_t* a_hi = smem + L::kAOff + stage * A_STAGE_BYTES_P + m * 128;
@@ -368,7 +394,8 @@ l2norm_project_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid
         for (int c = 0; c < 2; ++c) {
           const int chunk = (quarter * 2 + c) ^ (m & 7);  // 128B swizzle: 16-byte chunk index XOR row % 8
           *reinterpret_cast<uint4*>(a_hi + chunk * 16) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-          *reinterpret_cast<uint4*>(a_lo + chunk * 16) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+          if (!p.fast)
+            *reinterpret_cast<uint4*>(a_lo + chunk * 16) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
         __syncwarp();
@@ -1056,7 +1083,7 @@ int launch_project_kernel(const CUtensorMap& twh, const CUtensorMap& twl, const 
 }
 
 template <int NCTA>
-int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k, int normalize,
+int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k, int normalize, int fast,
                      const void* packed, float* out, cudaStream_t stream) {
   const PackedLayout l = packed_layout(E, k);
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
@@ -1084,6 +1111,15 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
   CUtensorMap tx = twh;
   p.prefetch = 0;
   p.rowmajor = 0;
+  p.fast = 0;
+  // single fp16 pass: only the staged pair kernel implements it; tmap for the fp16 weight copy
+  CUtensorMap twf = twh;
+  if (fast && NCTA == 2) {
+    rc = encode_tmap_2d(&twf, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, pk + l.h_off, static_cast<uint64_t>(l.k_pad),
+                        static_cast<uint64_t>(l.f_pad), static_cast<uint64_t>(l.f_pad) * 2,
+                        static_cast<uint32_t>(l.k_pad / NCTA), PK, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != ISX_OK) return rc;
+  }
   if constexpr (NCTA == 2) {
     // n x E row-major input (PCA.transform's flat vectors, the pooled rows): 2-D map, swizzled boxes
     if (hw == 1 && E % 4 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15u) == 0 && m_total < (1ll << 31)) {
@@ -1091,7 +1127,8 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
                           static_cast<uint64_t>(E), static_cast<uint64_t>(E) * 4, PM, 32, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc != ISX_OK) return rc;
       p.rowmajor = 1;
-      return launch_project_kernel<-1, 2>(twh, twl, tx, p, grid, stream);
+      p.fast = fast;
+      return launch_project_kernel<-1, 2>(fast ? twf : twh, twl, tx, p, grid, stream);
     }
   }
   const long long images = m_total / hw;
@@ -1110,6 +1147,10 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
     // reg = register-path loads without raw staging.  Read per call (a getenv, not on any hot loop).
     const char* mode_env = getenv("ISX_PROJECT_MODE");
     const int mode = (mode_env && mode_env[0] == 't') ? 0 : (mode_env && mode_env[0] == 'r') ? 2 : 1;
+    if (p.prefetch && fast) {
+      p.fast = 1;
+      return launch_project_kernel<-1, 2>(twf, twl, tx, p, grid, stream);
+    }
     if (p.prefetch && mode == 0) {
       auto kern = l2norm_project_tmem_kernel;
       const int smem = static_cast<int>(ProjTSmem::kDynamicBytes);
@@ -1137,13 +1178,15 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
 }
 
 int launch_project(const float* fmap, long long m_total, int E, int hw, int k, int normalize,
-                   const void* packed, float* out, cudaStream_t stream, const char* fn) {
+                   const void* packed, float* out, cudaStream_t stream, const char* fn, int fast = 0) {
   (void)fn;
   int sms = 148;
   int rc = device_sm_count(&sms);
   if (rc != ISX_OK) return rc;
-  if (sms >= 2 && project_ncta() == 2) return launch_project_n<2>(fmap, m_total, E, hw, k, normalize, packed, out, stream);
-  return launch_project_n<1>(fmap, m_total, E, hw, k, normalize, packed, out, stream);
+  // shapes the staged pair kernel cannot take run the exact three-pass kernels even when the fast
+  // mode was asked for (more accurate, never less)
+  if (sms >= 2 && project_ncta() == 2) return launch_project_n<2>(fmap, m_total, E, hw, k, normalize, fast, packed, out, stream);
+  return launch_project_n<1>(fmap, m_total, E, hw, k, normalize, 0, packed, out, stream);
 }
 
 }  // namespace
@@ -1174,6 +1217,7 @@ int isx_project_pack(const float* feature_means, const float* comps, int F, int 
   pack_weights_kernel<<<blocks, 256, 0, stream>>>(feature_means, comps, F, k, ld_f, ld_k, l.k_pad, l.f_pad,
                                                   reinterpret_cast<__nv_bfloat16*>(pk + l.hi_off),
                                                   reinterpret_cast<__nv_bfloat16*>(pk + l.lo_off),
+                                                  reinterpret_cast<__half*>(pk + l.h_off),
                                                   reinterpret_cast<float*>(pk + l.bias_off));
   ISX_CHECK_CUDA(cudaGetLastError());
   return ISX_OK;
@@ -1185,10 +1229,9 @@ size_t isx_l2norm_project_workspace_bytes(int B, int E, int h, int w, int k, int
   return static_cast<size_t>(B) * E * sizeof(float) + 256;  // pooled B x E vectors
 }
 
-int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, int normalize,
-                       const void* packed, int k, float* out, void* workspace, size_t workspace_bytes,
-                       isx_stream_t stream_) {
-  const char* fn = "isx_l2norm_project";
+static int l2norm_project_impl(const char* fn, int fast, const float* fmap, int B, int E, int h, int w, int pool,
+                               int normalize, const void* packed, int k, float* out, void* workspace,
+                               size_t workspace_bytes, isx_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ISX_REQUIRE(B > 0 && E > 0 && h > 0 && w > 0 && k > 0, "%s: dimensions must be positive (B=%d E=%d h=%d w=%d k=%d)",
               fn, B, E, h, w, k);
@@ -1199,7 +1242,7 @@ int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, 
   ISX_REQUIRE(hw < (1ll << 24) && static_cast<long long>(B) * hw < (1ll << 40), "%s: feature map too large", fn);
   if (!pool) {
     return launch_project(fmap, static_cast<long long>(B) * hw, E, static_cast<int>(hw), k, normalize, packed, out,
-                          stream, fn);
+                          stream, fn, fast);
   }
   ISX_REQUIRE(normalize, "%s: pool == 1 requires normalize == 1", fn);
   ISX_REQUIRE(E <= 64 * kPoolMaxAcc, "%s: pooled mode supports at most %d channels (E=%d)", fn, 64 * kPoolMaxAcc, E);
@@ -1232,7 +1275,21 @@ int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, 
     ISX_CHECK_CUDA(cudaGetLastError());
   }
   // project the pooled rows: an n x F matrix is a feature "map" with one cell per image
-  return launch_project(pooled, B, E, 1, k, /*normalize=*/0, packed, out, stream, fn);
+  return launch_project(pooled, B, E, 1, k, /*normalize=*/0, packed, out, stream, fn, fast);
+}
+
+int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, int normalize,
+                       const void* packed, int k, float* out, void* workspace, size_t workspace_bytes,
+                       isx_stream_t stream) {
+  return l2norm_project_impl("isx_l2norm_project", 0, fmap, B, E, h, w, pool, normalize, packed, k, out, workspace,
+                             workspace_bytes, stream);
+}
+
+int isx_l2norm_project_fp16(const float* fmap, int B, int E, int h, int w, int pool, int normalize,
+                            const void* packed, int k, float* out, void* workspace, size_t workspace_bytes,
+                            isx_stream_t stream) {
+  return l2norm_project_impl("isx_l2norm_project_fp16", 1, fmap, B, E, h, w, pool, normalize, packed, k, out,
+                             workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

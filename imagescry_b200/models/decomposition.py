@@ -137,18 +137,25 @@ class PCA(HParamsModule):
         _lib.check(rc, "isx_l2norm_project")
         return out
 
-    def project_feature_map(self, fmap: Float[Tensor, "B E H W"], *, pool: str | None = None) -> Tensor:
+    def project_feature_map(
+        self, fmap: Float[Tensor, "B E H W"], *, pool: str | None = None, precision: str = "exact"
+    ) -> Tensor:
         """Fused stage 2 on a backbone feature map: L2-normalise every cell over the channels
         (`embedding.py:74`), optionally mean-pool the cells, project (`decomposition.py:91`).
 
         pool=None  → B×k×h×w with NHWC strides, the exact tensor `pipelines.py:82-84` returns.
         pool="mean" → B×k.
+        precision="exact" → three-pass bf16 split (fp32-class products, ~1e-6 of a row's norm);
+        precision="fp16"  → one fp16 tensor pass (~1e-5 of a row's norm, |x| ≤ 65504): the kernel
+                            then runs at the HBM roofline instead of the tensor one.
         """
         if not self.fitted:
             raise RuntimeError("PCA model not fitted")
         _lib.require_cuda(fmap, "fmap")
         if pool not in (None, "mean"):
             raise ValueError(f"Invalid pool: {pool}")
+        if precision not in ("exact", "fp16"):
+            raise ValueError(f"Invalid precision: {precision}")
         B, E, h, w = fmap.shape
         if E != self.num_features:
             raise ValueError(f"feature map has {E} channels, PCA was fitted on {self.num_features}")
@@ -163,7 +170,8 @@ class PCA(HParamsModule):
             ws_bytes = lib.isx_l2norm_project_workspace_bytes(B, E, h, w, k, 1)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=f.device)
         if B > 0:
-            rc = lib.isx_l2norm_project(
+            entry = lib.isx_l2norm_project if precision == "exact" else lib.isx_l2norm_project_fp16
+            rc = entry(
                 f.data_ptr(), B, E, h, w, int(pool is not None), 1, self.packed_weights().data_ptr(), k,
                 out.data_ptr(), None if ws is None else ws.data_ptr(), ws_bytes, _lib.stream_ptr(f.device),
             )

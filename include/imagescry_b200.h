@@ -112,6 +112,14 @@ int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, 
                        const void* packed, int k, float* out, void* workspace,
                        size_t workspace_bytes, isx_stream_t stream);
 
+/* Same contract with ONE fp16 tensor pass instead of the three-pass bf16 split: feature values and
+ * weights are rounded to fp16 (11-bit significand; |x| saturates at 65504), fp32 accumulation.
+ * Error relative to a row's norm is ~1e-5 (bar: 1e-3); the kernel then runs at the HBM roofline
+ * instead of the tensor one.  Shapes the staged kernel cannot take fall back to the exact kernels. */
+int isx_l2norm_project_fp16(const float* fmap, int B, int E, int h, int w, int pool, int normalize,
+                            const void* packed, int k, float* out, void* workspace,
+                            size_t workspace_bytes, isx_stream_t stream);
+
 /* ---- PCA.fit moments (models/decomposition.py:94-148) -------------------------------------------
  * mean[F] = column means of x (n x F fp32, row-major; :116) and cov[F x F] = Xc^T Xc / (n - 1) with
  * Xc = x - mean centred in fp32 as the reference does (:119).  The eigenvectors / eigenvalues of cov

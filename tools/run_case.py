@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--case", default="resize256")
     ap.add_argument("--pool", default="none")
     ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--precision", default="exact")
     a = ap.parse_args()
     peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
     dev = torch.device("cuda", 0)
@@ -116,7 +117,7 @@ def main():
             del fmap
             ts = timeit(lambda: pca.transform(flat), a.iters, a.warm)
         else:
-            ts = timeit(lambda: pca.project_feature_map(fmap, pool=pool), a.iters, a.warm)
+            ts = timeit(lambda: pca.project_feature_map(fmap, pool=pool, precision=a.precision), a.iters, a.warm)
         ms = min(ts)
         gbs = algo / (ms * 1e-3) / 1e9
         print(json.dumps({"case": f"project pool={a.pool} B={B}", "ms": ts, "GBps": gbs, "frac_hbm": gbs / peaks["hbm_gbs"]}))
