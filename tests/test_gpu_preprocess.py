@@ -89,6 +89,7 @@ CASES = [
     (3, 3, 64, 64, (32, 32)),   # exact 2x down-scale: integer box path
     (2, 3, 48, 72, (24, 36)),   # box path (NHWC), rectangular; NCHW needs outW % 8 == 0
     (3, 3, 32, 80, (16, 40)),   # box path in both layouts
+    (1, 3, 6, 4128, (3, 2064)), # box path, rows wider than a CTA (several passes over q)
     (2, 3, 20, 44, (10, 22)),   # 2x but outW % 4 != 0: generic sampling kernel
     (2, 3, 96, 80, (37, 31)),
     (2, 3, 40, 48, (80, 96)),   # up-scale
