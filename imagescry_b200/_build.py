@@ -70,6 +70,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
+    # diagnostic builds only, e.g. ISX_NVCC_EXTRA="-DISX_KNN_PROFILE" python -m imagescry_b200._build --force
+    extra += os.environ.get("ISX_NVCC_EXTRA", "").split()
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")

@@ -413,6 +413,29 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
+// tcgen05.wait::ld that also names the 32 destination registers of the load it completes, so that no
+// use of them can be scheduled above the wait (needed once loads are software-pipelined and the wait
+// no longer follows its load directly).
+__device__ __forceinline__ void tc_wait_ld_regs(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// Packed fp32 multiply (FMUL2 on sm_100): (a0, a1) *= (w0, w1), each lane rounded to nearest like FMUL.
+__device__ __forceinline__ void mul_f32x2(uint32_t& a0, uint32_t& a1, float w0, float w1) {
+  uint64_t a, w, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(w) : "f"(w0), "f"(w1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(w));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(d));
+}
+
 // ----------------------------------------------------------------------------
 // Warp-cooperative bitonic sort of 32*E (score, index) pairs, element i = e*32 + lane.
 // Order: score descending, then index ascending (the oracle's tie-break).  NaN never wins.
@@ -461,6 +484,41 @@ __device__ __forceinline__ void warp_sort_desc(float (&s)[E], int (&idx)[E]) {
           const bool keep_mine = (desc_block == i_am_lower) ? mine_first : !mine_first;
           if (!keep_mine) { s[e] = os; idx[e] = oi; }
         }
+      }
+    }
+  }
+}
+
+// Final phase of the same network: sorts a BITONIC input (slots [0, T/2) descending, slots [T/2, T)
+// ascending, in the pair order above) with log2(T) compare-exchange steps instead of the full sort's
+// log2(T) (log2(T) + 1) / 2.  Used to merge two sorted lists.
+template <int E>
+__device__ __forceinline__ void warp_merge_desc(float (&s)[E], int (&idx)[E]) {
+  const uint32_t lane = lane_id();
+  constexpr int TOTAL = 32 * E;
+#pragma unroll
+  for (int j = TOTAL >> 1; j > 0; j >>= 1) {
+    if (j >= 32) {
+      const int je = j >> 5;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int pe = e ^ je;
+        if (pe > e) {
+          if (!pair_before(s[e], idx[e], s[pe], idx[pe])) {
+            float ts = s[e]; s[e] = s[pe]; s[pe] = ts;
+            int ti = idx[e]; idx[e] = idx[pe]; idx[pe] = ti;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float os = __shfl_xor_sync(kFullMask, s[e], j);
+        const int oi = __shfl_xor_sync(kFullMask, idx[e], j);
+        const bool i_am_lower = ((lane & j) == 0);
+        const bool mine_first = pair_before(s[e], idx[e], os, oi);
+        const bool keep_mine = i_am_lower ? mine_first : !mine_first;
+        if (!keep_mine) { s[e] = os; idx[e] = oi; }
       }
     }
   }

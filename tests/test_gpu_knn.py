@@ -85,6 +85,31 @@ def test_knn_vs_oracle(n, q, d, k):
         assert idx[0, :3].tolist() == [3, 17, n - 1][:k]
 
 
+@pytest.mark.parametrize("n,q,d,k", [(20000, 300, 256, 10), (9000, 140, 128, 100)])
+def test_knn_heterogeneous_norms(n, q, d, k):
+    """Store rows whose norms span four decades: the epilogue's chunk-level bound (raw maximum times
+    the chunk's largest inverse norm) is then loose, and the exact per-column scaling must decide."""
+    rng = np.random.default_rng(n + k)
+    store, queries = make(n, q, d, seed=n * 3 + k)
+    store = O.bf16_round(store * (10.0 ** rng.uniform(-2, 2, size=(n, 1))).astype(np.float32))
+    store[11] = 0.0
+    queries = O.bf16_round(queries * (10.0 ** rng.uniform(-1, 1, size=(q, 1))).astype(np.float32))
+    st = S.EmbeddingStore(torch.from_numpy(store).cuda())
+    scores, idx = st.search(torch.from_numpy(queries).cuda(), k)
+    check(store, queries, k, scores, idx)
+
+
+@pytest.mark.parametrize("n,q,k", [(150, 40, 128), (200, 300, 128), (20, 5, 16)])
+def test_knn_negative_thresholds(n, q, k):
+    """k close to n: the k-th best cosine is negative, where the chunk-level bound does not apply."""
+    store, queries = make(n, q, 64, seed=n + k)
+    st = S.EmbeddingStore(torch.from_numpy(store).cuda())
+    scores, idx = st.search(torch.from_numpy(queries).cuda(), k)
+    check(store, queries, k, scores, idx)
+    if k <= n:
+        assert (scores[:, k - 1] < 0).any()
+
+
 def test_knn_small_store_padding_and_index_base():
     store, queries = make(6, 5, 64, seed=1)
     st = S.EmbeddingStore(torch.from_numpy(store).cuda(), index_base=1000)
