@@ -265,9 +265,9 @@ __device__ __forceinline__ float thr_decode_below(uint32_t u) {
   return (f == 0.0f) ? __uint_as_float(0x80000001u) : f;
 }
 
-template <int THREADS>
-__device__ __forceinline__ void epilogue_bar_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+// one named barrier per epilogue group (its four warps stage and read their own 128 inverse norms)
+__device__ __forceinline__ void epilogue_bar_sync(int group) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
 }
 
 // Warp-cooperative prune of one row's candidate buffer: sort, keep the best k, return the new
@@ -290,17 +290,48 @@ __device__ __forceinline__ void prune_row(uint2* row_buf, int swz, int count, in
       idx[e] = INT_MAX;
     }
   }
-  warp_sort_desc<E>(s, idx);
-  float kth = -INFINITY;
+  if constexpr (E == 1) {
+    // 32 entries, one per lane: rank every entry by counting the entries that sort before it.  The
+    // 32 steps are independent (shuffle throughput, ~300 cycles) where the bitonic network is a chain
+    // of 15 dependent shuffle steps (~800): the prune sits on the path that gates the accumulator
+    // hand-off of all 16 epilogue warps of a pair.
+    const float ms = s[0];
+    const int mi = idx[0];
+    int rank = 0;
 #pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int i = e * 32 + lane;
-    if (i < k && i < count) row_buf[i ^ swz] = make_uint2(__float_as_uint(s[e]), static_cast<uint32_t>(idx[e]));
-    const float cand = __shfl_sync(kFullMask, s[e], (k - 1) & 31);
-    if (e == ((k - 1) >> 5)) kth = cand;
+    for (int j = 0; j < 32; ++j) {
+      const float os = __shfl_sync(kFullMask, ms, j);
+      const int oi = __shfl_sync(kFullMask, mi, j);
+      rank += pair_before(os, oi, ms, mi) ? 1 : 0;
+    }
+    new_count = min(count, k);
+    __syncwarp();
+    if (lane < count && rank < k) row_buf[rank ^ swz] = make_uint2(__float_as_uint(ms), static_cast<uint32_t>(mi));
+    __syncwarp();
+    // sorted order back into registers (slot i on lane i), as the callers expect
+    if (lane < new_count) {
+      const uint2 v = row_buf[lane ^ swz];
+      s[0] = __uint_as_float(v.x);
+      idx[0] = static_cast<int>(v.y);
+    } else {
+      s[0] = -INFINITY;
+      idx[0] = INT_MAX;
+    }
+    const float kth = __shfl_sync(kFullMask, s[0], (k - 1) & 31);
+    new_thr = (count >= k) ? kth : -INFINITY;
+  } else {
+    warp_sort_desc<E>(s, idx);
+    float kth = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = e * 32 + lane;
+      if (i < k && i < count) row_buf[i ^ swz] = make_uint2(__float_as_uint(s[e]), static_cast<uint32_t>(idx[e]));
+      const float cand = __shfl_sync(kFullMask, s[e], (k - 1) & 31);
+      if (e == ((k - 1) >> 5)) kth = cand;
+    }
+    new_count = min(count, k);
+    new_thr = (count >= k) ? kth : -INFINITY;
   }
-  new_count = min(count, k);
-  new_thr = (count >= k) ? kth : -INFINITY;
 }
 
 template <int CAP, int NCTA>
@@ -527,7 +558,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (row_valid) thr = fmaxf(thr, thr_decode_below(pre_thr));
         if (nb + 1 < nb1) prefetch_tile(nb + 1);
         ISX_PROF_BEGIN();
-        epilogue_bar_sync<kEpiThreads>();
+        epilogue_bar_sync(eg);
         ISX_PROF_END(5);
 
         // Selection of one 32-column chunk held in registers.  Fast path (almost every chunk): scale
@@ -667,6 +698,10 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             collect_chunk(rb, cb + 32, gb, vb);
           }
         }
+        // Off the hand-off path (the accumulator stage is already released): prune the rows whose
+        // buffers are more than half-way from k to full, so that a prune inside the next tiles' chunk
+        // loops — where it delays the release every other warp of the pair waits for — stays an exception.
+        prune_rows(__ballot_sync(kFullMask, 2 * cnt > CAP + p.k));
         ISX_PROF_END(6);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
