@@ -90,6 +90,9 @@ KnnPlan plan_knn(long long n, int q, int k, int sms_total, int ncta) {
     if (eff > best_eff + 1e-9) { best_eff = eff; best_s = static_cast<int>(s); }
     if (eff >= 0.97) break;
   }
+  // ISX_KNN_SPLITS forces the split count (tuning / A-B measurements)
+  static const int forced = [] { const char* e = getenv("ISX_KNN_SPLITS"); return e ? atoi(e) : 0; }();
+  if (forced > 0) best_s = static_cast<int>(std::min<long long>(forced, max_s));
   p.splits = best_s;
   p.items = static_cast<long long>(p.mb) * p.splits;
   p.grid = static_cast<int>(std::min<long long>(sms, p.items)) * ncta;
