@@ -160,6 +160,26 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
 int isx_topk_merge(const float* scores, const int32_t* idx, int g, int q, int k, float* out_scores,
                    int32_t* out_idx, isx_stream_t stream);
 
+/* ---- ROI masks on the feature-map grid ---------------------------------------
+ * geometry.py:14-65 `create_roi_mask`: rasterio.features.rasterize(shapes, out_shape=(hf, wf),
+ * transform=Affine.scale(w / wf, h / hf), fill=0, all_touched=True) * class_index.  rasterio / GDAL
+ * are third-party and absent from the reference tree; the rule implemented is "a cell is burned when
+ * its open rectangle shares positive area with a polygon" (cells that only touch a polygon along an
+ * edge or corner stay 0), which reproduces tests/test_geometry.py:10-52 and the docstring example.
+ *
+ * edges: fp32 [n_edges][4] = (x0, y0, x1, y1) in IMAGE coordinates, the closed rings (exterior and
+ * holes) of polygon p occupying edges [poly_offsets[p], poly_offsets[p + 1]).  mask: int64 fmap_h x
+ * fmap_w, class_index where burned, else 0 (Int64[H W], geometry.py:19). */
+int isx_roi_rasterize(const float* edges, const int32_t* poly_offsets, int n_poly, int image_h, int image_w,
+                      int fmap_h, int fmap_w, int64_t class_index, int64_t* mask, isx_stream_t stream);
+
+/* Masked pooling: out[b][e] = mean over the cells c with mask[c] == class_index of fmap[b][e][c]
+ * (0 when no cell matches).  fmap: fp32 B x E x h x w, what predict_step returns
+ * (models/embedding.py:57-76); mask: int64 h x w shared by all images (mask_per_image == 0) or
+ * B x h x w.  The result is the ROI's query vector for isx_knn_search.  No reference code. */
+int isx_masked_pool(const float* fmap, int B, int E, int h, int w, const int64_t* mask, int mask_per_image,
+                    int64_t class_index, float* out, isx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

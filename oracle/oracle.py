@@ -425,3 +425,106 @@ def knn_graph(store: np.ndarray, k: int) -> tuple[np.ndarray, np.ndarray]:
         keep = i[r] != r
         out_s[r], out_i[r] = s[r][keep][:k], i[r][keep][:k]
     return out_s, out_i
+
+
+# ------------------------------------------------------------------------------------------------
+# ROI masks.  /root/reference/src/imagescry/geometry.py:14-65 `create_roi_mask`
+# calls rasterio.features.rasterize(..., transform=Affine.scale(w / wf, h / hf), all_touched=True);
+# rasterio 1.4 / GDAL are third-party and absent from the reference tree, so this is a restatement —
+# PARITY UNPINNED beyond the reference's own expectations (tests/test_geometry.py:10-52 and the
+# docstring example at geometry.py:33-43, which tests/test_oracle_golden.py checks): a cell is
+# burned when the area of (polygon ∩ cell rectangle) is positive.  Formulated here by clipping every
+# ring to the cell (Sutherland-Hodgman) and summing signed areas — deliberately not the edge-crossing
+# / centre-parity test the CUDA kernel uses.
+# ------------------------------------------------------------------------------------------------
+def _polygon_rings(poly) -> list[list[tuple[float, float]]]:
+    """Rings of one polygon: a shapely-like object (.exterior.coords / .interiors), a dict with
+    'exterior' and optional 'interiors', or a plain vertex sequence."""
+    if hasattr(poly, "exterior"):
+        rings = [list(poly.exterior.coords)] + [list(r.coords) for r in poly.interiors]
+    elif isinstance(poly, dict):
+        rings = [list(poly["exterior"])] + [list(r) for r in poly.get("interiors", [])]
+    else:
+        rings = [list(poly)]
+    out = []
+    for r in rings:
+        pts = [(float(x), float(y)) for x, y in r]
+        if len(pts) > 1 and pts[0] == pts[-1]:
+            pts = pts[:-1]
+        out.append(pts)
+    return out
+
+
+def _clip_ring(ring, x0, y0, x1, y1):
+    def clip(pts, inside, intersect):
+        res = []
+        for a, b in zip(pts, pts[1:] + pts[:1]):
+            ia, ib = inside(a), inside(b)
+            if ia and ib:
+                res.append(b)
+            elif ia and not ib:
+                res.append(intersect(a, b))
+            elif not ia and ib:
+                res.append(intersect(a, b))
+                res.append(b)
+        return res
+
+    def at_x(x):
+        return lambda a, b: (x, a[1] + (b[1] - a[1]) * (x - a[0]) / (b[0] - a[0]))
+
+    def at_y(y):
+        return lambda a, b: (a[0] + (b[0] - a[0]) * (y - a[1]) / (b[1] - a[1]), y)
+
+    pts = list(ring)
+    for inside, inter in ((lambda p: p[0] >= x0, at_x(x0)), (lambda p: p[0] <= x1, at_x(x1)),
+                          (lambda p: p[1] >= y0, at_y(y0)), (lambda p: p[1] <= y1, at_y(y1))):
+        if not pts:
+            break
+        pts = clip(pts, inside, inter)
+    return pts
+
+
+def _ring_area(pts) -> float:
+    return 0.5 * sum(a[0] * b[1] - b[0] * a[1] for a, b in zip(pts, pts[1:] + pts[:1])) if len(pts) >= 3 else 0.0
+
+
+def create_roi_mask(roi, original_image_shape, feature_map_shape, class_index: int = 1) -> np.ndarray:
+    """geometry.py:14-65: int64 (hf, wf) mask, `class_index` where an ROI polygon overlaps the cell."""
+    h, w = original_image_shape
+    hf, wf = feature_map_shape
+    sx, sy = w / wf, h / hf
+    polys = roi if isinstance(roi, (list, tuple)) and roi and not _is_vertex(roi[0]) else [roi]
+    mask = np.zeros((hf, wf), dtype=np.int64)
+    for poly in polys:
+        rings = _polygon_rings(poly)
+        for i in range(hf):
+            for j in range(wf):
+                x0, x1, y0, y1 = j * sx, (j + 1) * sx, i * sy, (i + 1) * sy
+                area = 0.0
+                for n, ring in enumerate(rings):
+                    a = abs(_ring_area(_clip_ring(ring, x0, y0, x1, y1)))
+                    area += a if n == 0 else -a
+                if area > 1e-9 * sx * sy:
+                    mask[i, j] = class_index
+    return mask
+
+
+def _is_vertex(v) -> bool:
+    try:
+        return len(v) == 2 and all(isinstance(c, (int, float, np.integer, np.floating)) for c in v)
+    except TypeError:
+        return False
+
+
+def roi_pool(fmap: np.ndarray, mask: np.ndarray, class_index: int = 1) -> np.ndarray:
+    """Mean of the feature-map cells whose mask value is `class_index`: (B, E, h, w) -> (B, E);
+    mask (h, w) or (B, h, w).  Zero where no cell matches.  No reference code."""
+    fmap = np.asarray(fmap, dtype=np.float32)
+    b, e, h, w = fmap.shape
+    m = np.broadcast_to(np.asarray(mask) == class_index, (b, h, w)) if np.asarray(mask).ndim == 2 else (np.asarray(mask) == class_index)
+    out = np.zeros((b, e), dtype=np.float32)
+    for n in range(b):
+        cnt = int(m[n].sum())
+        if cnt:
+            out[n] = (fmap[n][:, m[n]].astype(np.float64).sum(axis=1) / cnt).astype(np.float32)
+    return out

@@ -245,3 +245,32 @@ def test_pca_fit_oracle_matches_reference_fit(golden, name, mev):
     ref_c = g[f"pca_{name}_comps"]
     dots = np.abs(np.sum(comps * ref_c, axis=0))  # same directions up to sign
     assert np.all(dots > 1 - 1e-4)
+
+
+# ---- ROI masks: the reference's own expectations, tests/test_geometry.py:10-52 ----
+def test_roi_mask_reference_single_polygon():
+    # test_create_roi_mask_single_polygon (and the docstring example, geometry.py:33-43)
+    mask = O.create_roi_mask([(0, 0), (4, 0), (4, 3), (0, 3)], (6, 8), (3, 4))
+    assert mask.shape == (3, 4) and mask.dtype == np.int64
+    assert np.array_equal(mask, np.array([[1, 1, 0, 0], [1, 1, 0, 0], [0, 0, 0, 0]]))
+
+
+def test_roi_mask_reference_multiple_polygons():
+    # test_create_roi_mask_multiple_polygons
+    roi = [[(0, 0), (1, 0), (1, 1), (0, 1)], [(2, 2), (3, 2), (3, 3), (2, 3)]]
+    mask = O.create_roi_mask(roi, (4, 4), (2, 2))
+    assert np.array_equal(mask, np.array([[1, 0], [0, 1]]))
+
+
+def test_roi_mask_class_index_holes_and_pool():
+    ring = [(2, 2), (14, 2), (14, 14), (2, 14)]
+    hole = [(5, 5), (11, 5), (11, 11), (5, 11)]
+    mask = O.create_roi_mask({"exterior": ring, "interiors": [hole]}, (16, 16), (8, 8), class_index=7)
+    assert set(np.unique(mask)) == {0, 7}
+    assert mask[3, 3] == 0 and mask[4, 4] == 0  # cells [6,8]x[6,8] and [8,10]x[8,10] lie inside the hole
+    assert mask[1, 1] == 7 and mask[2, 3] == 7 and mask[0, 0] == 0
+    fmap = np.arange(2 * 3 * 8 * 8, dtype=np.float32).reshape(2, 3, 8, 8)
+    pooled = O.roi_pool(fmap, mask, class_index=7)
+    assert pooled.shape == (2, 3)
+    assert np.allclose(pooled[1, 2], fmap[1, 2][mask == 7].mean())
+    assert np.array_equal(O.roi_pool(fmap, mask, class_index=3), np.zeros((2, 3), dtype=np.float32))
