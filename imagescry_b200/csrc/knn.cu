@@ -535,6 +535,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // prunes this one (the partial list may then hold fewer than k entries; the merge pads).
       float thr = row_valid ? -INFINITY : INFINITY;
       int cnt = 0;
+      float row_best = -INFINITY;  // best score this item has appended for the row
 
       // Per-tile staging runs one tile ahead: the store rows' inverse norms of tile nb + 1 and the
       // shared bound of this row are fetched into registers while tile nb is being selected, so their
@@ -638,6 +639,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     if (__uint_as_float(r[j]) > thr && cbase + j < ncols) {
                       my_buf[cnt ^ my_swz] = make_uint2(r[j], static_cast<uint32_t>(n0 + cbase + j));
                       ++cnt;
+                      row_best = fmaxf(row_best, __uint_as_float(r[j]));
                       ISX_PROF_COUNT(11, 1);
                     }
                   }
@@ -654,6 +656,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                   if (__uint_as_float(r[j]) > thr && cbase + j < ncols) {
                     my_buf[cnt ^ my_swz] = make_uint2(r[j], static_cast<uint32_t>(n0 + cbase + j));
                     ++cnt;
+                    row_best = fmaxf(row_best, __uint_as_float(r[j]));
                     ISX_PROF_COUNT(11, 1);
                   }
                 }
@@ -717,65 +720,174 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // of one item's rows (z = 3.1 sigma for 10 k rows against 4.3 sigma for the whole 1 M-row
       // store, i.e. 50 x as many survivors per chunk); with the running list the bound follows the
       // whole store seen so far.
+      // Rows whose best candidate is below the bound the grid has reached meanwhile cannot change
+      // their running list (the bound is a lower bound of the final k-th best; `>` against the value
+      // just below it keeps ties): they skip the sort, the lock and the merge — about half the rows
+      // of an item in steady state.
       ISX_PROF_BEGIN();
-      for (int rr = 0; rr < 32; ++rr) {
-        __syncwarp();
-        const int c = __shfl_sync(kFullMask, cnt, rr);
-        const int qr = m0 + ew * 32 + rr;
-        float nthr;
-        int ncnt;
-        prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr, ncnt,
-                       s_reg, i_reg);
-        if (qr < p.q && ncnt > 0) {  // warp-uniform
-          float* gs = p.run_scores + static_cast<size_t>(qr) * p.k;
-          int32_t* gi = p.run_idx + static_cast<size_t>(qr) * p.k;
-          if (lane == 0) {
-            uint64_t t0 = 0;
-            while (atomicCAS(p.run_lock + qr, 0u, 1u) != 0u) {
-              __nanosleep(64);
-              const uint64_t now = global_timer_ns();
-              if (t0 == 0) t0 = now;
-              else if (now - t0 > ISX_MBAR_TIMEOUT_NS) {
-                printf("isx: knn_search_kernel: running-list lock of query %d timed out\n", qr);
-                __trap();
-              }
-            }
-            __threadfence();
+      uint32_t todo;
+      {
+        const uint32_t bound_u = row_valid ? *reinterpret_cast<const volatile uint32_t*>(p.thr_shared + qrow) : 0u;
+        todo = __ballot_sync(kFullMask, row_valid && cnt > 0 && row_best > thr_decode_below(bound_u));
+      }
+      if constexpr (E == 1) {
+        // 32-entry buffers.  The per-row chain (sort, lock, fence, load, merge, store, fence, unlock) is
+        // mostly global-memory latency, so it is run in phases over all rows at once:
+        //  A  sort every row; the sorted best k stay in the row's shared-memory buffer;
+        //  B  every lane TRIES the lock of its own row once (no lane ever waits while the warp
+        //     holds a lock, so warps contending for the same rows cannot deadlock);
+        //  C  for the rows whose lock was taken, four at a time: issue the loads of four running
+        //     lists, then merge and write them back one after the other;
+        //  D  one fence, then every lane publishes its row's bound and releases its lock.
+        // Rows whose lock was busy go through B-D again.
+        {
+          uint32_t t = todo;
+          while (t) {
+            const int rr = __ffs(t) - 1;
+            t &= t - 1;
+            __syncwarp();
+            const int c = __shfl_sync(kFullMask, cnt, rr);
+            float nthr;
+            int ncnt;
+            prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr, ncnt,
+                           s_reg, i_reg);
+            if (lane == rr) cnt = ncnt;
           }
           __syncwarp();
-          // bitonic input: slots [0, k) this item's best (sorted descending), the running list
-          // reversed at the top (slot CAP-1-j = its j-th best), (-inf, none) in between
-#pragma unroll
-          for (int e = 0; e < E; ++e) {
-            const int i = e * 32 + lane;
-            if (i >= ncnt) { s_reg[e] = -INFINITY; i_reg[e] = INT_MAX; }
-            const int j = CAP - 1 - i;
-            if (j < p.k) {
-              const int id = __ldcg(gi + j);
-              const float sc = __ldcg(gs + j);
-              if (id >= 0) { s_reg[e] = sc; i_reg[e] = id; }
+        }
+        uint32_t pending = todo;
+        uint64_t t0 = 0;
+        while (pending) {
+          const bool mine = (pending >> lane) & 1u;
+          const bool got = mine && atomicCAS(p.run_lock + qrow, 0u, 1u) == 0u;
+          uint32_t gotm = __ballot_sync(kFullMask, got);
+          if (gotm == 0) {
+            __nanosleep(128);
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > ISX_MBAR_TIMEOUT_NS) {
+              if (lane == 0) printf("isx: knn_search_kernel: running-list locks timed out (rows %08x of block %d)\n", pending, m0);
+              __trap();
             }
+            continue;
           }
-          warp_merge_desc<E>(s_reg, i_reg);
-          float kth = -INFINITY;
-          bool kth_valid = false;
+          pending &= ~gotm;
+          __threadfence();
+          float kth_mine = -INFINITY;
+          bool kth_valid_mine = false;
+          const int slot = CAP - 1 - lane;  // the running list's entry this lane holds in the bitonic input
+          while (gotm) {
+            int rows[4];
+            float ls[4];
+            int li[4];
 #pragma unroll
-          for (int e = 0; e < E; ++e) {
-            const int i = e * 32 + lane;
-            if (i < p.k) {
-              const bool have = i_reg[e] != INT_MAX;
-              gs[i] = s_reg[e];
-              gi[i] = have ? i_reg[e] : -1;
+            for (int b = 0; b < 4; ++b) {
+              rows[b] = gotm ? __ffs(gotm) - 1 : -1;
+              if (gotm) gotm &= gotm - 1;
+              ls[b] = -INFINITY;
+              li[b] = -1;
+              if (rows[b] >= 0 && slot < p.k) {
+                const size_t base = static_cast<size_t>(m0 + ew * 32 + rows[b]) * p.k;
+                li[b] = __ldcg(p.run_idx + base + slot);
+                ls[b] = __ldcg(p.run_scores + base + slot);
+              }
             }
-            const float cs = __shfl_sync(kFullMask, s_reg[e], (p.k - 1) & 31);
-            const int ci = __shfl_sync(kFullMask, i_reg[e], (p.k - 1) & 31);
-            if (e == ((p.k - 1) >> 5)) { kth = cs; kth_valid = ci != INT_MAX; }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              if (rows[b] < 0) continue;  // warp-uniform
+              const int rr = rows[b];
+              const int c = __shfl_sync(kFullMask, cnt, rr);
+              const uint2* buf = warp_buf + static_cast<size_t>(rr) * cand_stride;
+              float sv = -INFINITY;
+              int iv = INT_MAX;
+              if (lane < c) {
+                const uint2 v = buf[lane ^ (L::kSmemCand ? rr : 0)];
+                sv = __uint_as_float(v.x);
+                iv = static_cast<int>(v.y);
+              }
+              if (li[b] >= 0) { sv = ls[b]; iv = li[b]; }
+              s_reg[0] = sv;
+              i_reg[0] = iv;
+              warp_merge_desc<E>(s_reg, i_reg);
+              const size_t base = static_cast<size_t>(m0 + ew * 32 + rr) * p.k;
+              if (lane < p.k) {
+                p.run_scores[base + lane] = s_reg[0];
+                p.run_idx[base + lane] = (i_reg[0] != INT_MAX) ? i_reg[0] : -1;
+              }
+              const float cs = __shfl_sync(kFullMask, s_reg[0], p.k - 1);
+              const int ci = __shfl_sync(kFullMask, i_reg[0], p.k - 1);
+              if (lane == rr) { kth_mine = cs; kth_valid_mine = ci != INT_MAX; }
+            }
           }
           __threadfence();
           __syncwarp();
-          if (lane == 0) {
-            if (kth_valid) atomicMax(p.thr_shared + qr, thr_encode(kth));
-            atomicExch(p.run_lock + qr, 0u);
+          if (got) {
+            if (kth_valid_mine) atomicMax(p.thr_shared + qrow, thr_encode(kth_mine));
+            atomicExch(p.run_lock + qrow, 0u);
+          }
+        }
+      } else {
+        while (todo) {
+          const int rr = __ffs(todo) - 1;
+          todo &= todo - 1;
+          __syncwarp();
+          const int c = __shfl_sync(kFullMask, cnt, rr);
+          const int qr = m0 + ew * 32 + rr;
+          float nthr;
+          int ncnt;
+          prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr, ncnt,
+                         s_reg, i_reg);
+          if (qr < p.q && ncnt > 0) {  // warp-uniform
+            float* gs = p.run_scores + static_cast<size_t>(qr) * p.k;
+            int32_t* gi = p.run_idx + static_cast<size_t>(qr) * p.k;
+            if (lane == 0) {
+              uint64_t t0 = 0;
+              while (atomicCAS(p.run_lock + qr, 0u, 1u) != 0u) {
+                __nanosleep(64);
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > ISX_MBAR_TIMEOUT_NS) {
+                  printf("isx: knn_search_kernel: running-list lock of query %d timed out\n", qr);
+                  __trap();
+                }
+              }
+              __threadfence();
+            }
+            __syncwarp();
+            // bitonic input: slots [0, k) this item's best (sorted descending), the running list
+            // reversed at the top (slot CAP-1-j = its j-th best), (-inf, none) in between
+  #pragma unroll
+            for (int e = 0; e < E; ++e) {
+              const int i = e * 32 + lane;
+              if (i >= ncnt) { s_reg[e] = -INFINITY; i_reg[e] = INT_MAX; }
+              const int j = CAP - 1 - i;
+              if (j < p.k) {
+                const int id = __ldcg(gi + j);
+                const float sc = __ldcg(gs + j);
+                if (id >= 0) { s_reg[e] = sc; i_reg[e] = id; }
+              }
+            }
+            warp_merge_desc<E>(s_reg, i_reg);
+            float kth = -INFINITY;
+            bool kth_valid = false;
+  #pragma unroll
+            for (int e = 0; e < E; ++e) {
+              const int i = e * 32 + lane;
+              if (i < p.k) {
+                const bool have = i_reg[e] != INT_MAX;
+                gs[i] = s_reg[e];
+                gi[i] = have ? i_reg[e] : -1;
+              }
+              const float cs = __shfl_sync(kFullMask, s_reg[e], (p.k - 1) & 31);
+              const int ci = __shfl_sync(kFullMask, i_reg[e], (p.k - 1) & 31);
+              if (e == ((p.k - 1) >> 5)) { kth = cs; kth_valid = ci != INT_MAX; }
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+              if (kth_valid) atomicMax(p.thr_shared + qr, thr_encode(kth));
+              atomicExch(p.run_lock + qr, 0u);
+            }
           }
         }
       }
