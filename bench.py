@@ -589,6 +589,7 @@ def run_b200(args) -> None:
                 cpu_baseline = {"error": repr(ex)}
     if dist_on and not args.no_extra:
         extra["sharded_large"] = bench_sharded_large(args, world, rank, dev, peaks)
+        extra["sharded_graph"] = bench_sharded_graph(world, rank, dev, peaks)
 
     if rank == 0:
         line = {
@@ -605,6 +606,32 @@ def run_b200(args) -> None:
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_sharded_graph(world: int, rank: int, dev, peaks: dict, rows: int = 1_000_000, dim: int = 256, k: int = 10) -> dict:
+    """The search step of BASELINE.json config 5: all-pairs k=10 similarity graph over a 1 M x 256
+    bf16 store row-sharded over the ranks; all rows are replicated once over NVLink as queries, each
+    rank searches them against its shard, one all-gather + merge per 131072-row block."""
+    import torch
+
+    from imagescry_b200.search import ShardedEmbeddingStore, shard_range
+
+    b, e = shard_range(rows, world, rank)
+    g = torch.Generator(device=dev).manual_seed(77)
+    full = torch.randn((rows, dim), generator=g, device=dev).to(torch.bfloat16)  # identical on every rank
+    store = ShardedEmbeddingStore(full[b:e].contiguous(), total_rows=rows)
+    del full
+    sec = timed_steps(lambda: store.knn_graph(k), 2, 1, True)
+    tf = 2.0 * rows * (e - b) * dim / sec / 1e12
+    peak_sus = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    out = {
+        "workload": f"all-pairs k={k} graph, {rows}x{dim} bf16 store row-sharded over {world} GPUs, all rows replicated as queries",
+        "graph_rows_per_s": rows / sec, "ms": sec * 1e3, "per_gpu_tflops_incl_collectives": tf,
+        "frac_of_sustained_bf16_peak": tf / peak_sus, "frac_of_burst_bf16_peak": tf / peaks["bf16_tflops"],
+    }
+    del store
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_sharded_large(args, world: int, rank: int, dev, peaks: dict) -> dict:

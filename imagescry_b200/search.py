@@ -209,6 +209,7 @@ class ShardedEmbeddingStore:
                     f"rank {self.rank} should hold rows [{begin}, {end}) but got {local_embeddings.shape[0]} rows"
                 )
             index_base = begin
+        self.total_rows = total_rows
         self.local = EmbeddingStore(local_embeddings, index_base=index_base)
 
     def search(self, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
@@ -216,6 +217,46 @@ class ShardedEmbeddingStore:
         all_s, all_i = gather_partials(scores, idx, self.group)
         s, i = merge_topk(all_s, all_i, k)
         return s, i.to(torch.int64)
+
+    def replicated_rows(self) -> Tensor:
+        """The whole store on every rank (bf16 N x d): one all-gather of the shards over NVLink.
+        BASELINE.json config 5 replicates the 1 M x 256 store (512 MB) as the all-pairs queries.
+        Shards may differ by one row (`shard_range`); they are padded to the longest for the gather."""
+        import torch.distributed as dist
+
+        sizes = [e - b for b, e in (shard_range(self.total_rows, self.world_size, r) for r in range(self.world_size))]
+        per = max(sizes)
+        local = self.local.embeddings
+        d = local.shape[1]
+        padded = torch.zeros((per, d), dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
+        out = torch.empty((per * self.world_size, d), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, padded, group=self.group)
+        if all(sz == per for sz in sizes):
+            return out
+        return torch.cat([out[r * per: r * per + sizes[r]] for r in range(self.world_size)], dim=0)
+
+    def knn_graph(self, k: int, *, block: int = 131072) -> tuple[Tensor, Tensor]:
+        """All-pairs similarity graph over the sharded store (BASELINE.json config 5): every rank
+        searches ALL rows (replicated once over NVLink) against its shard in blocks with k + 1,
+        one all-gather of (score, index) + merge per block, self matches removed.  Every rank
+        returns the full graph: (scores N x k fp32, indices N x k int64)."""
+        if self.total_rows is None:
+            raise ValueError("knn_graph needs a store built with total_rows (the contiguous partition)")
+        rows_all = self.replicated_rows()
+        n = rows_all.shape[0]
+        rn_all = row_rnorm(rows_all)
+        dev = rows_all.device
+        out_s = torch.empty((n, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((n, k), dtype=torch.int64, device=dev)
+        for b in range(0, n, block):
+            e = min(n, b + block)
+            s, i = self.local.search_raw(rows_all[b:e], k + 1, query_rnorm=rn_all[b:e])
+            all_s, all_i = gather_partials(s, i, self.group)
+            s, i = merge_topk(all_s, all_i, k + 1)
+            s, i = drop_self_matches(s, i.to(torch.int64), torch.arange(b, e, device=dev), k)
+            out_s[b:e], out_i[b:e] = s, i
+        return out_s, out_i
 
     def replicate_queries(self, host_queries: Tensor) -> Tensor:
         """Replicated device copy of a (pinned) host query matrix without sending it over PCIe once

@@ -44,6 +44,17 @@ for k in (10, 100):
     assert np.abs(s.cpu().numpy() - rs).max() <= 1e-3
     assert (i.cpu().numpy() == ri).mean() > 0.995
     assert i[0, :2].tolist() == [7, 29000]
+# all-pairs graph over the sharded store (config 5) == the single-GPU graph
+from imagescry_b200.search import knn_graph
+gn = 5003
+gstore = O.bf16_round(rng.standard_normal((gn, 64)).astype(np.float32))
+gstore[11] = gstore[4000]
+gb, ge = shard_range(gn, world, rank)
+gs, gi = ShardedEmbeddingStore(torch.from_numpy(gstore[gb:ge]).cuda(), total_rows=gn).knn_graph(10, block=2048)
+fs, fi = knn_graph(EmbeddingStore(torch.from_numpy(gstore).cuda()), 10, block=2048)
+assert torch.equal(gi, fi) and torch.allclose(gs, fs, atol=1e-6), rank
+assert not (gi == torch.arange(gn, device=gi.device).reshape(-1, 1)).any()
+assert int(gi[11, 0]) == 4000 and int(gi[4000, 0]) == 11
 dist.barrier()
 dist.destroy_process_group()
 print("OK", rank)
