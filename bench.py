@@ -580,6 +580,10 @@ def run_b200(args) -> None:
             except Exception as ex:
                 extra["project"] = {"error": repr(ex)}
             try:
+                extra["search_other_shapes"] = bench_search_shapes(store, queries, peaks)
+            except Exception as ex:
+                extra["search_other_shapes"] = {"error": repr(ex)}
+            try:
                 extra["sift_small"] = bench_sift_small()
             except Exception as ex:
                 extra["sift_small"] = {"error": repr(ex)}
@@ -606,6 +610,31 @@ def run_b200(args) -> None:
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_search_shapes(store, queries, peaks: dict) -> dict:
+    """The other search shapes BASELINE.json names, on one GPU: k = 100 over the metric's store
+    (config 4's k) and k = 10 over a 1 M x 256 store (config 5's dimensionality)."""
+    import torch
+
+    from imagescry_b200.search import EmbeddingStore
+
+    peak_sus = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+
+    def run(st, q, k):
+        sec = timed_steps(lambda: st.search_raw(q, k), 5, 3, False)
+        tf = 2.0 * q.shape[0] * len(st) * st.dim / sec / 1e12
+        return {"queries_per_s": q.shape[0] / sec, "ms": sec * 1e3, "tflops": tf,
+                "frac_of_sustained_bf16_peak": tf / peak_sus, "frac_of_burst_bf16_peak": tf / peaks["bf16_tflops"]}
+
+    out = {"k100_d1280": run(store, queries, 100)}
+    dev = queries.device
+    st256 = EmbeddingStore(device_randn_bf16(N_STORE, 256, 1234, dev))
+    out["k10_d256"] = run(st256, device_randn_bf16(Q, 256, 4321, dev), 10)
+    out["store"] = f"{N_STORE} rows, {Q} queries"
+    del st256
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_sharded_graph(world: int, rank: int, dev, peaks: dict, rows: int = 1_000_000, dim: int = 256, k: int = 10) -> dict:
