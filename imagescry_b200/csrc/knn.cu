@@ -679,7 +679,9 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // (Loading a group's whole 128-column share first and releasing the stage before any selection
         // was measured too: slower, d = 256 5.8 ms against 4.6 — the epilogue is bound by its own
         // instruction stream, ~180 scheduler cycles per 32 columns of which the inverse-norm loads and
-        // multiplies are 64, not by the hand-off.)
+        // multiplies are 64, not by the hand-off.  A bound per 4-column group — raw group maximum times
+        // the group's largest inverse norm, 30 instructions per chunk in front of the exact scaling —
+        // does not pay either: for N(0, 1) rows it passes about twice as often as the exact test.)
         uint32_t ra[32], rb[32];
 #pragma unroll 1
         for (int ld = 0; ld < kGroupCols / 32; ld += 2) {
