@@ -87,18 +87,25 @@ class PCA(HParamsModule):
         return f"{self.__class__.__name__}(num_features={num_features}, num_components={num_components})"
 
     # ------------------------------------------------------------------ packed weights
-    def packed_weights(self) -> Tensor:
-        """bf16 hi/lo split of `component_vectors` plus the bias -(means . components), in the layout
-        the projection kernel's TMA descriptors read.  Rebuilt when the parameters change."""
+    def _param_key(self) -> tuple:
+        """Identity of the fitted parameters (storage, version counter, shape) — no device access."""
         cv, fm = self.component_vectors, self.feature_means
-        _lib.require_cuda(cv, "PCA parameters")
+
         def version(t: Tensor) -> int:
             try:
                 return t._version
             except RuntimeError:  # inference tensors (fitted under torch.inference_mode) have no counter
                 return -1
 
-        key = (cv.data_ptr(), fm.data_ptr(), version(cv), version(fm), tuple(cv.shape), tuple(cv.stride()), str(cv.device))
+        return (cv.data_ptr(), fm.data_ptr(), version(cv), version(fm), tuple(cv.shape), tuple(cv.stride()), str(cv.device))
+
+    def packed_weights(self) -> Tensor:
+        """bf16 hi/lo split of `component_vectors` plus the bias -(means . components), in the layout
+        the projection kernel's TMA descriptors read.  Rebuilt when the parameters change."""
+        cv = self.component_vectors
+        _lib.require_cuda(cv, "PCA parameters")
+        fm = self.feature_means
+        key = self._param_key()
         if self._packed is None or self._packed_key != key:
             lib = _lib.load()
             F, k = cv.shape
@@ -149,17 +156,25 @@ class PCA(HParamsModule):
         precision="fp16"  → one fp16 tensor pass (~1e-5 of a row's norm, |x| ≤ 65504): the kernel
                             then runs at the HBM roofline instead of the tensor one.
         """
-        if not self.fitted:
-            raise RuntimeError("PCA model not fitted")
+        # `fitted`, `num_features` and `num_components` are scalar parameters (decomposition.py keeps
+        # them in the state dict); reading them is a device synchronisation each, and three per call
+        # left the GPU idle for ~16 % of a pooled-projection step.  The fitted flag is therefore
+        # re-read only when the parameters changed, and the sizes come from the weight matrix
+        # (`fit` stores exactly num_features x num_components of it, decomposition.py:139-146).
+        key = self._param_key()
+        if getattr(self, "_fitted_key", None) != key:
+            if not self.fitted:
+                raise RuntimeError("PCA model not fitted")
+            self._fitted_key = key
         _lib.require_cuda(fmap, "fmap")
         if pool not in (None, "mean"):
             raise ValueError(f"Invalid pool: {pool}")
         if precision not in ("exact", "fp16"):
             raise ValueError(f"Invalid precision: {precision}")
         B, E, h, w = fmap.shape
-        if E != self.num_features:
-            raise ValueError(f"feature map has {E} channels, PCA was fitted on {self.num_features}")
-        k = self.num_components
+        num_features, k = self.component_vectors.shape
+        if E != num_features:
+            raise ValueError(f"feature map has {E} channels, PCA was fitted on {num_features}")
         f = fmap.float().contiguous()
         lib = _lib.load()
         if pool is None:
