@@ -232,20 +232,24 @@ struct KnnParams {
 // Shared-memory plan.  k <= kSmallK: 32-entry per-row candidate buffers live in shared memory next to
 // a 4-stage operand ring (the buffers are XOR-swizzled by row so that 32 rows appending at the same
 // depth hit different banks).  Larger k: 256-entry buffers in the global workspace.
-template <int CAP, int NCTA>
+template <int CAP, int NCTA, bool RES_ = false>
 struct KnnSmem {
+  // RES: the query tile (all k-blocks, at most kResKb = 4, i.e. d <= 256) stays resident in shared
+  // memory for a whole item and the ring holds store tiles only: half the operand traffic per tile.
+  static constexpr bool RES = RES_;
+  static constexpr int kResKb = 4;
   static constexpr uint32_t B_STAGE_BYTES = (BN / NCTA) * BK * 2;  // 32 KB, or 16 KB per CTA of a pair
   static constexpr int G = epi_groups(CAP);
-  static constexpr int STAGES = (NCTA == 2) ? (CAP <= 32 ? 5 : 6) : (CAP <= 32 ? 3 : 4);
+  static constexpr int STAGES = RES ? 6 : (NCTA == 2) ? (CAP <= 32 ? 5 : 6) : (CAP <= 32 ? 3 : 4);
   static constexpr bool kSmemCand = (CAP <= 32);
   static constexpr int CHUNK = kSmemCand ? 16 : 32;  // accumulator columns per selection window
   static constexpr uint32_t kCandBytes = kSmemCand ? G * BM * CAP * 8 : 0;
   static constexpr uint32_t kAOff = 0;
-  static constexpr uint32_t kBOff = kAOff + STAGES * A_STAGE_BYTES;
+  static constexpr uint32_t kBOff = kAOff + (RES ? kResKb : STAGES) * A_STAGE_BYTES;
   static constexpr uint32_t kCandOff = kBOff + STAGES * B_STAGE_BYTES;
   static constexpr uint32_t kRnormOff = kCandOff + kCandBytes;            // [ACC_STAGES][BN] floats
   static constexpr uint32_t kBarOff = kRnormOff + ACC_STAGES * BN * 4;    // mbarriers
-  static constexpr uint32_t kNumBars = 2 * STAGES + 2 * ACC_STAGES;
+  static constexpr uint32_t kNumBars = 2 * STAGES + 2 * ACC_STAGES + 2;  // + resident-query full / empty
   static constexpr uint32_t kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr uint32_t kTotal = kTmemPtrOff + 16;
   // the operand tiles need 1024-byte alignment; the dynamic window normally starts aligned, so only
@@ -337,11 +341,11 @@ __device__ __forceinline__ void prune_row(uint2* row_buf, int swz, int count, in
   }
 }
 
-template <int CAP, int NCTA>
+template <int CAP, int NCTA, bool RES>
 __global__ void __launch_bounds__(knn_threads(CAP), 1)
 knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
                   const KnnParams p) {
-  using L = KnnSmem<CAP, NCTA>;
+  using L = KnnSmem<CAP, NCTA, RES>;
   constexpr int STAGES = L::STAGES;
   constexpr int kEpiGroups = L::G;
   constexpr int kEpiThreads = 128 * kEpiGroups;
@@ -367,6 +371,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + ACC_STAGES;
+  uint64_t* a_full = bars + 2 * STAGES + 2 * ACC_STAGES;
+  uint64_t* a_empty = a_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
   float* rnorm_s = reinterpret_cast<float*>(smem + L::kRnormOff);
 
@@ -384,6 +390,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], NCTA); mbar_init(&empty_bar[i], 1); }
+    mbar_init(a_full, NCTA);
+    mbar_init(a_empty, 1);
     for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * kEpiGroups * NCTA); }
     fence_mbar_init();
   }
@@ -409,12 +417,24 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // DRAM reads 37.8 GB -> ~5 GB per pass, 23.5 -> 21 ms.  ISX_KNN_WINDOW overrides the window.
       const uint32_t kThrottleEvery = p.throttle_every;  // a power of two
       const uint32_t kThrottleWindow = p.throttle_window;
-      uint32_t seq = 0;
+      uint32_t seq = 0, item_no = 0;
       for (long long item = unit; item < p.items; item += num_units) {
         const int split = static_cast<int>(item / p.mb);
         const int mblk = static_cast<int>(item - static_cast<long long>(split) * p.mb);
         const long long nb0 = p.nb * split / p.splits, nb1 = p.nb * (split + 1) / p.splits;
         const int32_t m0 = (mblk * NCTA + static_cast<int>(rank)) * BM;
+        if (RES) {
+          // resident query tile: wait until the previous item's MMAs have read it, then load all k-blocks
+          mbar_wait(a_empty, (item_no & 1u) ^ 1u);
+          if (NCTA == 2) mbar_arrive_expect_tx_leader(a_full, static_cast<uint32_t>(num_kb) * A_STAGE_BYTES);
+          else mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(num_kb) * A_STAGE_BYTES);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            uint8_t* a_res = smem + L::kAOff + kb * A_STAGE_BYTES;
+            if (NCTA == 2) tma_load_2d_pair(a_res, &tmap_q, a_full, kb * BK, m0, kEvictLast);
+            else tma_load_2d(a_res, &tmap_q, a_full, kb * BK, m0, kEvictLast);
+          }
+          ++item_no;
+        }
         for (long long nb = nb0; nb < nb1; ++nb, ++seq) {
           if ((seq & (kThrottleEvery - 1)) == 0) {
             volatile uint32_t* prog = p.progress;
@@ -442,16 +462,17 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             ISX_PROF_BEGIN();
             mbar_wait(&empty_bar[stage], phase ^ 1);
             ISX_PROF_END(0);
-            uint8_t* a_dst = smem + L::kAOff + stage * A_STAGE_BYTES;
+            uint8_t* a_dst = smem + L::kAOff + (RES ? 0 : stage) * A_STAGE_BYTES;
             uint8_t* b_dst = smem + L::kBOff + stage * B_STAGE_BYTES;
+            constexpr uint32_t kStageTx = (RES ? 0u : A_STAGE_BYTES) + B_STAGE_BYTES;
             if (NCTA == 2) {
               // both CTAs report to the leader's barrier (count 2, 2 x 32 KB of transactions)
-              mbar_arrive_expect_tx_leader(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-              tma_load_2d_pair(a_dst, &tmap_q, &full_bar[stage], kb * BK, m0, kEvictLast);
+              mbar_arrive_expect_tx_leader(&full_bar[stage], kStageTx);
+              if (!RES) tma_load_2d_pair(a_dst, &tmap_q, &full_bar[stage], kb * BK, m0, kEvictLast);
               tma_load_2d_pair(b_dst, &tmap_e, &full_bar[stage], kb * BK, n0, kEvictNormal);
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-              tma_load_2d(a_dst, &tmap_q, &full_bar[stage], kb * BK, m0, kEvictLast);
+              mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
+              if (!RES) tma_load_2d(a_dst, &tmap_q, &full_bar[stage], kb * BK, m0, kEvictLast);
               tma_load_2d(b_dst, &tmap_e, &full_bar[stage], kb * BK, n0, kEvictNormal);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -465,10 +486,15 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // ===================== MMA issuer =====================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, BM * NCTA, BN);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, item_no = 0;
       for (long long item = unit; item < p.items; item += num_units) {
         const int split = static_cast<int>(item / p.mb);
         const long long nb0 = p.nb * split / p.splits, nb1 = p.nb * (split + 1) / p.splits;
+        if (RES) {
+          mbar_wait(a_full, item_no & 1u);
+          tc_fence_after();
+          ++item_no;
+        }
         for (long long nb = nb0; nb < nb1; ++nb) {
           ISX_PROF_BEGIN();
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -480,7 +506,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             mbar_wait(&full_bar[stage], phase);
             ISX_PROF_END(3);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + L::kAOff + stage * A_STAGE_BYTES);
+            const uint32_t a_addr = smem_u32(smem + L::kAOff + (RES ? kb : static_cast<int>(stage)) * A_STAGE_BYTES);
             const uint32_t b_addr = smem_u32(smem + L::kBOff + stage * B_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -497,6 +523,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           if (NCTA == 2) tc_commit_pair(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        // the resident query tile may be overwritten once every MMA of this item has read it
+        if (RES) { if (NCTA == 2) tc_commit_pair(a_empty); else tc_commit(a_empty); }
       }
       ISX_PROF_FLUSH(2);
       ISX_PROF_FLUSH(3);
@@ -1012,10 +1040,10 @@ KnnWorkspace knn_workspace(const KnnPlan& plan, int q, int k) {
   return w;
 }
 
-template <int CAP, int NCTA>
+template <int CAP, int NCTA, bool RES = false>
 int launch_search(const CUtensorMap& tq, const CUtensorMap& te, const KnnParams& p, int grid, cudaStream_t stream) {
-  auto kern = knn_search_kernel<CAP, NCTA>;
-  const int smem = static_cast<int>(KnnSmem<CAP, NCTA>::kDynamicBytes);
+  auto kern = knn_search_kernel<CAP, NCTA, RES>;
+  const int smem = static_cast<int>(KnnSmem<CAP, NCTA, RES>::kDynamicBytes);
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -1171,7 +1199,10 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
   p.debug_skip_select = getenv("ISX_KNN_SKIP_SELECT") ? atoi(getenv("ISX_KNN_SKIP_SELECT")) : 0;
 #endif
   if (ncta == 2) {
-    if (k <= kSmallK) rc = launch_search<32, 2>(tq, te, p, plan.grid, stream);
+    // short rows, small k: the query tile stays resident (ISX_KNN_RESIDENT=0 switches it off)
+    static const bool no_res = [] { const char* e = getenv("ISX_KNN_RESIDENT"); return e && e[0] == '0'; }();
+    if (k <= kSmallK && d <= 256 && !no_res) rc = launch_search<32, 2, true>(tq, te, p, plan.grid, stream);
+    else if (k <= kSmallK) rc = launch_search<32, 2>(tq, te, p, plan.grid, stream);
     else rc = launch_search<256, 2>(tq, te, p, plan.grid, stream);
   } else {
     if (k <= kSmallK) rc = launch_search<32, 1>(tq, te, p, plan.grid, stream);
