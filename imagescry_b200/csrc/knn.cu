@@ -789,6 +789,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
           __syncwarp();
         }
+        ISX_PROF_COUNT(14, __popc(todo));
+        ISX_PROF_BEGIN1();
         uint32_t pending = todo;
         uint64_t t0 = 0;
         while (pending) {
@@ -859,7 +861,9 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if (kth_valid_mine) atomicMax(p.thr_shared + qrow, thr_encode(kth_mine));
             atomicExch(p.run_lock + qrow, 0u);
           }
+          ISX_PROF_COUNT(15, 1);
         }
+        ISX_PROF_END1(13);
       } else {
         while (todo) {
           const int rr = __ffs(todo) - 1;
@@ -930,7 +934,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
     if (warp == kEpilogueWarp0 && lane == 0 && rank == 0) {
       ISX_PROF_FLUSH(4); ISX_PROF_FLUSH(5); ISX_PROF_FLUSH(6); ISX_PROF_FLUSH(8);
-      ISX_PROF_FLUSH(9); ISX_PROF_FLUSH(10); ISX_PROF_FLUSH(12); ISX_PROF_FLUSH(13);
+      ISX_PROF_FLUSH(9); ISX_PROF_FLUSH(10); ISX_PROF_FLUSH(12); ISX_PROF_FLUSH(13); ISX_PROF_FLUSH(14); ISX_PROF_FLUSH(15);
     }
 #ifdef ISX_KNN_PROFILE
     if (warp == kEpilogueWarp0 && rank == 0) {  // appends: summed over the warp's 32 rows
@@ -1225,8 +1229,9 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
             h[8] / units / tiles);
     fprintf(stderr,
             "isx knn profile (warp 4 of every leader CTA, per tile): chunks %.2f, with survivors %.3f, appends %.3f, "
-            "prunes %.3f, cycles in the rare path %.0f\n",
-            h[9] / units / tiles, h[10] / units / tiles, h[11] / units / tiles, h[12] / units / tiles, h[13] / units / tiles);
+            "prunes %.3f, cycles in the rare path + item-end lock/merge phases %.0f; per item: rows merged %.1f, lock rounds %.1f\n",
+            h[9] / units / tiles, h[10] / units / tiles, h[11] / units / tiles, h[12] / units / tiles, h[13] / units / tiles,
+            h[14] / units / (static_cast<double>(plan.items) / units), h[15] / units / (static_cast<double>(plan.items) / units));
   }
 #endif
   // finalize: scale the running lists by the queries' inverse norms, rebase the rows, order by the
