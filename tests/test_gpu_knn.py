@@ -72,6 +72,9 @@ def check(store, queries, k, scores, idx, index_base=0):
         (2000, 257, 128, 10),    # CTA pairs: the second pair holds one query row
         (2500, 513, 64, 100),    # CTA pairs with global candidate buffers, ragged store tile
         (60000, 1000, 256, 32),  # pairs x splits x k between the two candidate-buffer regimes
+        (20000, 19000, 64, 10),  # more query blocks than units: several items per unit (resident query tile reloaded)
+        (9000, 700, 200, 16),    # resident query tile with a ragged last k-block
+        (5000, 300, 8, 5),       # one k-block, mostly zero-filled
     ],
 )
 def test_knn_vs_oracle(n, q, d, k):
