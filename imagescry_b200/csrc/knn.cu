@@ -348,7 +348,6 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   using L = KnnSmem<CAP, NCTA, RES>;
   constexpr int STAGES = L::STAGES;
   constexpr int kEpiGroups = L::G;
-  constexpr int kEpiThreads = 128 * kEpiGroups;
   constexpr int kGroupCols = BN / kEpiGroups;
   constexpr uint32_t B_STAGE_BYTES = L::B_STAGE_BYTES;
   // NCTA == 2: this CTA and its cluster peer form one MMA of M = 256 (cta_group::2).  Rank r owns
