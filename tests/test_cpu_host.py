@@ -216,3 +216,38 @@ def test_store_format_codec_matches_reference_wire_format():
         F.maps_to_rows(stacked)  # CPU tensor: the conversion runs on the GPU only
     img, cell = F.rows_to_image_cell([0, 11, 12, 25], 12)
     assert img.tolist() == [0, 0, 1, 2] and cell.tolist() == [0, 11, 0, 1]
+
+
+def test_polygon_edges_host_logic():
+    """geometry.polygon_edges: the edge list handed to isx_roi_rasterize, for every accepted polygon
+    form (vertex list, closed ring, dict with holes, shapely-like object, list of polygons)."""
+    from imagescry_b200 import geometry as G
+
+    sq = [(0, 0), (4, 0), (4, 3), (0, 3)]
+    e, off = G.polygon_edges(sq)
+    assert e.dtype == np.float32 and e.shape == (4, 4) and off.tolist() == [0, 4]
+    assert e[0].tolist() == [0, 0, 4, 0] and e[3].tolist() == [0, 3, 0, 0]  # the ring is closed
+    e2, off2 = G.polygon_edges(sq + [sq[0]])  # shapely repeats the first vertex
+    assert np.array_equal(e, e2) and off2.tolist() == [0, 4]
+    hole = [(1, 1), (2, 1), (2, 2)]
+    e3, off3 = G.polygon_edges({"exterior": sq, "interiors": [hole]})
+    assert e3.shape == (7, 4) and off3.tolist() == [0, 7]
+
+    class Ring:
+        def __init__(self, pts):
+            self.coords = pts
+
+    class Poly:  # duck-typed shapely.geometry.Polygon
+        def __init__(self, ext, holes=()):
+            self.exterior, self.interiors = Ring(ext), [Ring(h) for h in holes]
+
+    e4, off4 = G.polygon_edges([Poly(sq, [hole]), Poly(hole)])
+    assert off4.tolist() == [0, 7, 10] and np.array_equal(e4[:7], e3)
+    e5, off5 = G.polygon_edges([sq, hole])  # list of plain vertex lists = two polygons
+    assert off5.tolist() == [0, 4, 7]
+    with pytest.raises(ValueError):
+        G.polygon_edges([(0, 0), (1, 1)])
+    with pytest.raises(RuntimeError):  # no CPU rasteriser: the product path needs the GPU
+        G.create_roi_mask(sq, (6, 8), (3, 4), device="cpu")
+    with pytest.raises(ValueError):
+        G.create_roi_mask(sq, (6, 8), (0, 4), device="cpu")
