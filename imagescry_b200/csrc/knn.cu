@@ -414,9 +414,12 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // publishes how many tiles it has loaded and waits until the slowest unit is within
       // kThrottleWindow tiles (all units are co-resident: grid <= #SMs, one CTA per SM).  k = 100:
       // DRAM reads 37.8 GB -> ~5 GB per pass, 23.5 -> 21 ms.  ISX_KNN_WINDOW overrides the window.
+      // Units are normally co-resident (grid <= #SMs, one CTA per SM); the wait gives up after 2 ms.
       const uint32_t kThrottleEvery = p.throttle_every;  // a power of two
       const uint32_t kThrottleWindow = p.throttle_window;
       uint32_t seq = 0, item_no = 0;
+      bool throttle_on = true;
+      constexpr uint64_t kThrottleGiveUpNs = 2000000;  // 2 ms: above the longest item end (k = 100: ~0.3 ms)
       for (long long item = unit; item < p.items; item += num_units) {
         const int split = static_cast<int>(item / p.mb);
         const int mblk = static_cast<int>(item - static_cast<long long>(split) * p.mb);
@@ -438,7 +441,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           if ((seq & (kThrottleEvery - 1)) == 0) {
             volatile uint32_t* prog = p.progress;
             if (rank == 0) prog[unit] = seq;
-            if (seq > kThrottleWindow) {
+            if (throttle_on && seq > kThrottleWindow) {
               ISX_PROF_BEGIN();
               uint64_t t0 = 0;
               while (true) {
@@ -448,9 +451,12 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 __nanosleep(256);
                 const uint64_t now = global_timer_ns();
                 if (t0 == 0) t0 = now;
-                else if (now - t0 > ISX_MBAR_TIMEOUT_NS) {
-                  printf("isx: knn_search_kernel: lockstep throttle timed out (unit %lld seq %u slowest %u)\n", unit, seq, slowest);
-                  __trap();
+                else if (now - t0 > kThrottleGiveUpNs) {
+                  // The throttle is an optimisation, never a dependency: if some unit is this far
+                  // behind (its CTA pair has not been scheduled yet because another kernel holds SMs,
+                  // or it is stuck behind a long item end), stop synchronising for the rest of the launch.
+                  throttle_on = false;
+                  break;
                 }
               }
               ISX_PROF_END(1);
