@@ -4,8 +4,9 @@
 //   K4  knn_search_kernel  tcgen05 GEMM  S = Q . E^T  (bf16 operands from TMA-filled shared memory,
 //                          fp32 accumulators in TMEM) with the per-query top-k fused into the
 //                          epilogue: the Q x N score matrix never leaves the SM.
-//   K5  topk_merge_kernel  merges partial top-k lists (N-splits of one GPU, or the shards of
-//                          several GPUs after the NCCL all-gather).
+//   K5  topk_merge_kernel  finalises K4's running lists (scale by the queries' inverse norms, rebase
+//                          the rows) and merges the partial lists of several GPUs after the NCCL
+//                          all-gather.
 //
 // There is no reference implementation of this stage; semantics follow
 // oracle/oracle.py::cosine_knn: normalize(q) . normalize(e) with F.normalize's eps
@@ -13,7 +14,8 @@
 //
 // K4 structure (one persistent CTA per SM; CTA pairs when there are at least two query blocks):
 //   warp 0      TMA producer: query tile 128 x 64 and store tile 256 x 64 (bf16, 128B swizzle) per
-//               k-block into a STAGES-deep shared-memory ring
+//               k-block into a STAGES-deep shared-memory ring (short rows, d <= 256 and k <= 16: the
+//               query tile stays resident for a whole item and the ring carries store tiles only)
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma 128 x 256 x 16 (256 x 256 x 16 per
 //               pair), accumulating a 128 x 256 fp32 tile in one of two TMEM accumulator stages
 //   warp 2      TMEM allocation / deallocation
@@ -21,8 +23,8 @@
 //               epilogue: tcgen05.ld the finished tile 64 columns at a time (one query row per
 //               thread), scale by the store rows' inverse norms (FMUL2), reject everything below the
 //               row's running k-th best with one warp-uniform compare, append the rare survivors to a
-//               per-row candidate buffer and prune that buffer with a warp-cooperative bitonic sort
-//               when it is full.
+//               per-row candidate buffer and prune that buffer warp-cooperatively (rank counting for
+//               32 entries, bitonic sort for 256) when it is full.
 // Work decomposition: items = (N-split, query block); a unit walks items in split-major order so
 // that units running at the same time stream the same store rows and share them through L2.  At the
 // end of an item every row's best k are merged (per-query lock, bitonic merge) into the query's
