@@ -251,3 +251,34 @@ def test_polygon_edges_host_logic():
         G.create_roi_mask(sq, (6, 8), (3, 4), device="cpu")
     with pytest.raises(ValueError):
         G.create_roi_mask(sq, (6, 8), (0, 4), device="cpu")
+
+
+def test_binding_matches_header_prototypes():
+    """Every ctypes signature in imagescry_b200/_lib.py has the argument count, and pointer / integer /
+    float kinds, of its prototype in include/imagescry_b200.h (a mismatch would corrupt a call silently)."""
+    import ctypes
+
+    from imagescry_b200 import _lib
+
+    header = open(os.path.join(REPO, "include", "imagescry_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = dict(re.findall(r"\b(isx_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+
+    def kind(decl: str) -> str:
+        decl = decl.strip()
+        if "*" in decl or decl.startswith("isx_stream_t"):
+            return "ptr"
+        if decl.startswith(("float", "double")):
+            return "float"
+        return "int"
+
+    ckind = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_float: "float", ctypes.c_double: "float"}
+    for name, args in protos.items():
+        params = [] if args.strip() in ("", "void") else [a for a in args.split(",")]
+        _, argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} parameters, binding {len(argtypes)}"
+        for i, (decl, ct) in enumerate(zip(params, argtypes)):
+            want = kind(decl)
+            got = "ptr" if hasattr(ct, "contents") else ckind.get(ct, "int")
+            assert want == got, f"{name} argument {i} ({decl.strip()}): header {want}, binding {got}"
