@@ -25,6 +25,10 @@ LAYOUT_NHWC = 1
 DTYPE_U8 = 0
 DTYPE_F32 = 1
 DTYPE_BF16 = 2
+KNN_CONTINUE = 1
+KNN_NO_FINALIZE = 2
+KNN_EXCLUDE_SELF = 4
+KNN_PACKED = 8
 
 # name -> (restype, argtypes); mirrors include/imagescry_b200.h one to one
 SIGNATURES: dict[str, tuple] = {
@@ -41,6 +45,16 @@ SIGNATURES: dict[str, tuple] = {
         [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float,
          c_int, c_float, c_int, c_float, c_void_p, c_int, c_void_p],
     ),
+    "isx_preprocess_patches_stats": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+         c_void_p],
+    ),
+    "isx_preprocess_patches_apply": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
+         c_float, c_int, c_float, c_void_p, c_int, c_void_p],
+    ),
     "isx_resize_bilinear": (
         c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     ),
@@ -55,6 +69,7 @@ SIGNATURES: dict[str, tuple] = {
         c_int,
         [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
+    "isx_l2norm_cells": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "isx_pca_moments_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "isx_pca_moments": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "isx_row_rnorm_bf16": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
@@ -65,7 +80,13 @@ SIGNATURES: dict[str, tuple] = {
         [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p,
          c_void_p, c_size_t, c_void_p],
     ),
+    "isx_knn_search_ex": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p,
+         c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
     "isx_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "isx_topk_merge_packed": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "isx_roi_rasterize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p]),
     "isx_masked_pool": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
 }
@@ -124,3 +145,31 @@ def stream_ptr(device) -> int:
     import torch
 
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """Context manager for one C-ABI call: makes the operands' device the CURRENT device (the library
+    launches on the current device, reads its SM count and encodes its tensor maps there) and yields
+    the pointer of that device's current stream.  Operands on different devices are rejected —
+    the reference is plain torch and raises for mixed devices too."""
+
+    def __init__(self, *tensors) -> None:
+        import torch
+
+        devs = {t.device for t in tensors if t is not None}
+        if len(devs) != 1:
+            raise ValueError(f"all operands of one call must live on the same CUDA device, got {sorted(map(str, devs))}")
+        (self.device,) = devs
+        if self.device.type != "cuda":
+            raise RuntimeError(
+                f"operands must be CUDA tensors (got device {self.device}); imagescry_b200 runs on the GPU only "
+                "and has no CPU fallback"
+            )
+        self._guard = torch.cuda.device(self.device)
+
+    def __enter__(self) -> int:
+        self._guard.__enter__()
+        return stream_ptr(self.device)
+
+    def __exit__(self, *exc):
+        return self._guard.__exit__(*exc)

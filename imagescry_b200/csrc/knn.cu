@@ -195,11 +195,12 @@ struct KnnParams {
   long long n;
   int mb, splits;
   long long nb, items;
-  long long index_base;
+  int index_base;   // added to a store row when it enters a candidate buffer: the lists hold GLOBAL rows
+  int self_base;    // >= 0: query row r is store row self_base + r and never its own neighbour; -1: off
   const float* store_rnorm;
   const float* query_rnorm;
   float* run_scores;   // [q][k] running top-k of every query: raw scores (before the query's inverse norm)
-  int32_t* run_idx;    // [q][k] store rows (shard-local), -1 = empty slot
+  int32_t* run_idx;    // [q][k] global store rows (index_base + shard-local row), -1 = empty slot
   uint32_t* run_lock;  // [q]
   uint2* cand_global;  // [grid][BM][CAP] when k > kSmallK
   uint32_t* thr_shared;  // [q] per-query lower bound on the global k-th best (ordered-uint encoding)
@@ -564,6 +565,10 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const int m0 = (mblk * NCTA + static_cast<int>(rank)) * BM;
       const int qrow = m0 + row;
       const bool row_valid = qrow < p.q;
+      // all-pairs graph: the query is itself a store row and must not be its own neighbour.  The test
+      // sits in the rare path only (a query's own score is its maximum, so the tile that holds it
+      // always takes that path once and appends nothing for it).
+      const int self_row = (p.self_base >= 0) ? p.self_base + qrow : -1;
       // `thr`: a candidate must beat it.  It is the larger of this item's own k-th best and the
       // bound every CTA working on the same query publishes in thr_shared: anything below the k-th
       // best of ANY subset of the store cannot be in the global top-k, so other splits' progress
@@ -589,6 +594,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (long long nb = nb0; nb < nb1; ++nb) {
         const long long n0 = nb * BN;
         const int ncols = static_cast<int>(min(static_cast<long long>(BN), p.n - n0));
+        const int gcol0 = static_cast<int>(n0) + p.index_base;  // global row of the tile's first column
         // publish this tile's inverse norms (the previous user of this slot was tile nb-2, whose
         // readers all passed the barrier of tile nb-1)
         float* rn = rnorm_s + acc * BN;
@@ -671,8 +677,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const int j = 4 * gi + e;
-                    if (__uint_as_float(r[j]) > thr && cbase + j < ncols) {
-                      my_buf[cnt ^ my_swz] = make_uint2(r[j], static_cast<uint32_t>(n0 + cbase + j));
+                    if (__uint_as_float(r[j]) > thr && cbase + j < ncols && gcol0 + cbase + j != self_row) {
+                      my_buf[cnt ^ my_swz] = make_uint2(r[j], static_cast<uint32_t>(gcol0 + cbase + j));
                       ++cnt;
                       row_best = fmaxf(row_best, __uint_as_float(r[j]));
                       ISX_PROF_COUNT(11, 1);
@@ -688,8 +694,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               if (vmax > thr) {
 #pragma unroll
                 for (int j = h * CHUNK; j < (h + 1) * CHUNK; ++j) {
-                  if (__uint_as_float(r[j]) > thr && cbase + j < ncols) {
-                    my_buf[cnt ^ my_swz] = make_uint2(r[j], static_cast<uint32_t>(n0 + cbase + j));
+                  if (__uint_as_float(r[j]) > thr && cbase + j < ncols && gcol0 + cbase + j != self_row) {
+                    my_buf[cnt ^ my_swz] = make_uint2(r[j], static_cast<uint32_t>(gcol0 + cbase + j));
                     ++cnt;
                     row_best = fmaxf(row_best, __uint_as_float(r[j]));
                     ISX_PROF_COUNT(11, 1);
@@ -969,11 +975,14 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 // ------------------------------------------------------------------------------------------
 // K5: merge g sorted-or-not partial lists per query into the final top-k.  One warp per query.
 // ------------------------------------------------------------------------------------------
+// Partial lists come either as two arrays (scores fp32, idx int32) or — idx == nullptr — as packed
+// 8-byte records {fp32 score, int32 index} (what one all-gather moves); the result likewise
+// (out_idx == nullptr: packed records at out_scores).
 template <int CAP>
 __global__ void __launch_bounds__(128)
 topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, int g, int q, int k,
-                  const float* __restrict__ query_scale, long long index_base,
-                  float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+                  const float* __restrict__ query_scale, float* __restrict__ out_scores,
+                  int32_t* __restrict__ out_idx) {
   constexpr int E = CAP / 32;
   const int lane = threadIdx.x & 31;
   const int query = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -982,8 +991,9 @@ topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
   // remaining CAP - keep slots are refilled with fresh candidates
   const int keep = k;
   const int fresh = CAP - keep;
-  // the search's running lists hold raw scores and shard-local rows: scale and rebase them here
+  // the search's running lists hold raw scores: scale them by the query's inverse norm here
   const float qscale = query_scale ? query_scale[query] : 1.0f;
+  const uint2* rec = reinterpret_cast<const uint2*>(scores);
   float s[E];
   int id[E];
 #pragma unroll
@@ -1000,8 +1010,13 @@ topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
         if (c < total) {
           const long long part = c / k, j = c - part * k;
           const size_t off = (static_cast<size_t>(part) * q + query) * k + j;
-          const int raw = idx[off];
-          if (raw >= 0) { sv = scores[off] * qscale; iv = raw + static_cast<int>(index_base); }
+          if (idx) {
+            const int raw = idx[off];
+            if (raw >= 0) { sv = scores[off] * qscale; iv = raw; }
+          } else {
+            const uint2 v = rec[off];
+            if (static_cast<int>(v.y) >= 0) { sv = __uint_as_float(v.x) * qscale; iv = static_cast<int>(v.y); }
+          }
         }
         s[e] = sv;
         id[e] = iv;
@@ -1014,20 +1029,23 @@ topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
     const int pos = e * 32 + lane;
     if (pos < k) {
       const bool have = id[e] != INT_MAX;
-      out_scores[static_cast<size_t>(query) * k + pos] = have ? s[e] : -INFINITY;
-      out_idx[static_cast<size_t>(query) * k + pos] = have ? id[e] : -1;
+      const float sv = have ? s[e] : -INFINITY;
+      const int iv = have ? id[e] : -1;
+      const size_t o = static_cast<size_t>(query) * k + pos;
+      if (out_idx) { out_scores[o] = sv; out_idx[o] = iv; }
+      else reinterpret_cast<uint2*>(out_scores)[o] = make_uint2(__float_as_uint(sv), static_cast<uint32_t>(iv));
     }
   }
 }
 
 int launch_merge(const float* scores, const int32_t* idx, int g, int q, int k, const float* query_scale,
-                 long long index_base, float* out_scores, int32_t* out_idx, cudaStream_t stream) {
+                 float* out_scores, int32_t* out_idx, cudaStream_t stream) {
   const int warps_per_block = 4;
   const int blocks = (q + warps_per_block - 1) / warps_per_block;
   if (k <= 32)
-    topk_merge_kernel<64><<<blocks, 128, 0, stream>>>(scores, idx, g, q, k, query_scale, index_base, out_scores, out_idx);
+    topk_merge_kernel<64><<<blocks, 128, 0, stream>>>(scores, idx, g, q, k, query_scale, out_scores, out_idx);
   else
-    topk_merge_kernel<256><<<blocks, 128, 0, stream>>>(scores, idx, g, q, k, query_scale, index_base, out_scores, out_idx);
+    topk_merge_kernel<256><<<blocks, 128, 0, stream>>>(scores, idx, g, q, k, query_scale, out_scores, out_idx);
   ISX_CHECK_CUDA(cudaGetLastError());
   return ISX_OK;
 }
@@ -1038,7 +1056,9 @@ struct KnnWorkspace {
   size_t run_scores_off, run_idx_off, zero_off, zero_bytes, cand_off, total;
 };
 
-KnnWorkspace knn_workspace(const KnnPlan& plan, int q, int k) {
+// Offsets depend on (q, k) only — not on the store block — so that a search can be CONTINUED over
+// several store blocks with the same workspace (ISX_KNN_CONTINUE).  `max_grid` = the SM count.
+KnnWorkspace knn_workspace(int max_grid, int q, int k) {
   KnnWorkspace w;
   size_t off = 0;
   w.run_scores_off = off;
@@ -1049,7 +1069,7 @@ KnnWorkspace knn_workspace(const KnnPlan& plan, int q, int k) {
   w.zero_bytes = (2 * static_cast<size_t>(q) + 256) * sizeof(uint32_t);
   off = align_up(off + w.zero_bytes, 256);
   w.cand_off = off;
-  if (k > kSmallK) off = align_up(off + static_cast<size_t>(plan.grid) * epi_groups(256) * BM * 256 * sizeof(uint2), 256);
+  if (k > kSmallK) off = align_up(off + static_cast<size_t>(max_grid) * epi_groups(256) * BM * 256 * sizeof(uint2), 256);
   w.total = off + 256;
   return w;
 }
@@ -1138,38 +1158,53 @@ size_t isx_knn_workspace_bytes(int64_t n, int q, int d, int k) {
   if (n <= 0 || q <= 0 || k <= 0 || k > kMaxK) return 0;
   int sms = 148;
   if (device_sm_count(&sms) != ISX_OK) sms = 148;
-  // cover either scheduling mode (the choice may be overridden at search time)
-  return std::max(knn_workspace(plan_knn(n, q, k, sms, 1), q, k).total, knn_workspace(plan_knn(n, q, k, sms, 2), q, k).total);
+  return knn_workspace(sms, q, k).total;
 }
 
-int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const void* queries,
-                   const float* query_rnorm, int q, int d, int k, int64_t index_base,
-                   float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes,
-                   isx_stream_t stream_) {
-  const char* fn = "isx_knn_search";
+int isx_knn_search_ex(const void* store, const float* store_rnorm, int64_t n, const void* queries,
+                      const float* query_rnorm, int q, int d, int k, int64_t index_base,
+                      int64_t query_index_base, int flags, float* out_scores, int32_t* out_idx,
+                      void* workspace, size_t workspace_bytes, isx_stream_t stream_) {
+  const char* fn = "isx_knn_search_ex";
+  const bool cont = (flags & ISX_KNN_CONTINUE) != 0, finalize = (flags & ISX_KNN_NO_FINALIZE) == 0;
+  const bool packed = (flags & ISX_KNN_PACKED) != 0, no_self = (flags & ISX_KNN_EXCLUDE_SELF) != 0;
+  ISX_REQUIRE((flags & ~(ISX_KNN_CONTINUE | ISX_KNN_NO_FINALIZE | ISX_KNN_EXCLUDE_SELF | ISX_KNN_PACKED)) == 0,
+              "%s: unknown flag bits 0x%x", fn, flags);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ISX_REQUIRE(q > 0 && d > 0 && k > 0 && n >= 0, "%s: need q, d, k > 0 and n >= 0 (q=%d d=%d k=%d n=%lld)", fn, q, d, k, (long long)n);
   ISX_REQUIRE(k <= kMaxK, "%s: k = %d exceeds the supported maximum of %d", fn, k, kMaxK);
   ISX_REQUIRE(d % 8 == 0, "%s: d = %d must be a multiple of 8 (16-byte rows for TMA)", fn, d);
   ISX_REQUIRE(n < (1ll << 31) - BN, "%s: at most 2^31 store rows per call (n=%lld); shard the store", fn, (long long)n);
   ISX_REQUIRE(index_base >= 0 && index_base + n < (1ll << 31), "%s: index_base + n must fit in int32", fn);
-  ISX_REQUIRE(queries && query_rnorm && out_scores && out_idx, "%s: null pointer", fn);
+  ISX_REQUIRE(queries && query_rnorm, "%s: null pointer", fn);
+  ISX_REQUIRE(!finalize || (out_scores && (packed || out_idx)), "%s: null output pointer", fn);
+  ISX_REQUIRE(!no_self || (query_index_base >= 0 && query_index_base + q < (1ll << 31)),
+              "%s: query_index_base + q must fit in int32 (got %lld)", fn, (long long)query_index_base);
   ISX_REQUIRE((reinterpret_cast<uintptr_t>(queries) & 15u) == 0 && (reinterpret_cast<uintptr_t>(store) & 15u) == 0,
               "%s: store and queries must be 16-byte aligned", fn);
-  if (n == 0) {
-    // nothing to search: the merge of zero lists writes (-inf, -1) everywhere
-    return launch_merge(out_scores, out_idx, 0, q, k, nullptr, 0, out_scores, out_idx, stream);
-  }
-  ISX_REQUIRE(store && store_rnorm, "%s: null store pointer", fn);
   int sms = 148;
   int rc = device_sm_count(&sms);
   if (rc != ISX_OK) return rc;
-  const int ncta = (sms >= 2) ? knn_ncta(q) : 1;
-  const KnnPlan plan = plan_knn(n, q, k, sms, ncta);
-  const KnnWorkspace ws = knn_workspace(plan, q, k);
+  const KnnWorkspace ws = knn_workspace(sms, q, k);
   ISX_REQUIRE(workspace != nullptr && workspace_bytes >= ws.total, "%s: workspace too small (%zu < %zu)", fn,
               workspace_bytes, ws.total);
   uint8_t* wbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  float* run_scores = reinterpret_cast<float*>(wbase + ws.run_scores_off);
+  int32_t* run_idx = reinterpret_cast<int32_t*>(wbase + ws.run_idx_off);
+  uint32_t* zero_base = reinterpret_cast<uint32_t*>(wbase + ws.zero_off);
+  if (!cont) {
+    // a new search: empty running lists, no bounds, no locks
+    ISX_CHECK_CUDA(cudaMemsetAsync(zero_base, 0, ws.zero_bytes, stream));
+    ISX_CHECK_CUDA(cudaMemsetAsync(run_idx, 0xFF, static_cast<size_t>(q) * k * sizeof(int32_t), stream));
+  }
+  if (n == 0) {
+    // nothing to search in this block: the lists stay as they are
+    if (!finalize) return ISX_OK;
+    return launch_merge(run_scores, run_idx, 1, q, k, query_rnorm, out_scores, packed ? nullptr : out_idx, stream);
+  }
+  ISX_REQUIRE(store && store_rnorm, "%s: null store pointer", fn);
+  const int ncta = (sms >= 2) ? knn_ncta(q) : 1;
+  const KnnPlan plan = plan_knn(n, q, k, sms, ncta);
 
   CUtensorMap tq, te;
   rc = encode_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, queries, static_cast<uint64_t>(q),
@@ -1182,15 +1217,18 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
   KnnParams p;
   p.q = q; p.d = d; p.k = k; p.n = n;
   p.mb = plan.mb; p.splits = plan.splits; p.nb = plan.nb; p.items = plan.items;
-  p.index_base = index_base;
+  p.index_base = static_cast<int>(index_base);
+  p.self_base = no_self ? static_cast<int>(query_index_base) : -1;
   p.store_rnorm = store_rnorm;
   p.query_rnorm = query_rnorm;
-  p.run_scores = reinterpret_cast<float*>(wbase + ws.run_scores_off);
-  p.run_idx = reinterpret_cast<int32_t*>(wbase + ws.run_idx_off);
+  p.run_scores = run_scores;
+  p.run_idx = run_idx;
   p.cand_global = reinterpret_cast<uint2*>(wbase + ws.cand_off);
-  p.thr_shared = reinterpret_cast<uint32_t*>(wbase + ws.zero_off);
+  p.thr_shared = zero_base;
   p.progress = p.thr_shared + q;
   p.run_lock = p.progress + 256;
+  // a continued search keeps the lists and the bounds they imply; only the lockstep counters restart
+  if (cont) ISX_CHECK_CUDA(cudaMemsetAsync(p.progress, 0, 256 * sizeof(uint32_t), stream));
   // Lockstep window in tiles: measured best 16-32 at d = 1280 (640 KB of store rows per tile); it is a
   // footprint in L2, so it scales with 1/d, and the poll interval (a third of it, rounded down to a
   // power of two) with it: one poll reads every unit's counter, ~1 us, against 0.6 us per tile at d = 256.
@@ -1202,8 +1240,6 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
     while (every * 2 <= p.throttle_window / 3 && every < 1024) every *= 2;
     p.throttle_every = every;
   }
-  ISX_CHECK_CUDA(cudaMemsetAsync(p.thr_shared, 0, ws.zero_bytes, stream));
-  ISX_CHECK_CUDA(cudaMemsetAsync(p.run_idx, 0xFF, static_cast<size_t>(q) * k * sizeof(int32_t), stream));
 
 #ifdef ISX_KNN_PROFILE
   static unsigned long long* d_prof = nullptr;
@@ -1244,9 +1280,18 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
             h[14] / units / (static_cast<double>(plan.items) / units), h[15] / units / (static_cast<double>(plan.items) / units));
   }
 #endif
-  // finalize: scale the running lists by the queries' inverse norms, rebase the rows, order by the
-  // final (score desc, row asc)
-  return launch_merge(p.run_scores, p.run_idx, 1, q, k, query_rnorm, index_base, out_scores, out_idx, stream);
+  if (!finalize) return ISX_OK;
+  // finalize: scale the running lists by the queries' inverse norms, order by the final
+  // (score desc, row asc); packed: one 8-byte record per hit (what a single all-gather moves)
+  return launch_merge(p.run_scores, p.run_idx, 1, q, k, query_rnorm, out_scores, packed ? nullptr : out_idx, stream);
+}
+
+int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const void* queries,
+                   const float* query_rnorm, int q, int d, int k, int64_t index_base,
+                   float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes,
+                   isx_stream_t stream) {
+  return isx_knn_search_ex(store, store_rnorm, n, queries, query_rnorm, q, d, k, index_base, 0, 0, out_scores,
+                           out_idx, workspace, workspace_bytes, stream);
 }
 
 int isx_topk_merge(const float* scores, const int32_t* idx, int g, int q, int k, float* out_scores,
@@ -1256,7 +1301,19 @@ int isx_topk_merge(const float* scores, const int32_t* idx, int g, int q, int k,
   ISX_REQUIRE(g >= 0 && q > 0 && k > 0, "%s: need g >= 0, q > 0, k > 0 (g=%d q=%d k=%d)", fn, g, q, k);
   ISX_REQUIRE(k <= kMaxK, "%s: k = %d exceeds the supported maximum of %d", fn, k, kMaxK);
   ISX_REQUIRE(out_scores && out_idx && (g == 0 || (scores && idx)), "%s: null pointer", fn);
-  return launch_merge(scores, idx, g, q, k, nullptr, 0, out_scores, out_idx, stream);
+  return launch_merge(scores, idx, g, q, k, nullptr, out_scores, out_idx, stream);
+}
+
+int isx_topk_merge_packed(const void* records, int g, int q, int k, float* out_scores, int32_t* out_idx,
+                          isx_stream_t stream_) {
+  const char* fn = "isx_topk_merge_packed";
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ISX_REQUIRE(g >= 0 && q > 0 && k > 0, "%s: need g >= 0, q > 0, k > 0 (g=%d q=%d k=%d)", fn, g, q, k);
+  ISX_REQUIRE(k <= kMaxK, "%s: k = %d exceeds the supported maximum of %d", fn, k, kMaxK);
+  ISX_REQUIRE(out_scores && out_idx && (g == 0 || records), "%s: null pointer", fn);
+  ISX_REQUIRE((reinterpret_cast<uintptr_t>(records) & 7u) == 0, "%s: records must be 8-byte aligned", fn);
+  if (g == 0) return launch_merge(out_scores, out_idx, 0, q, k, nullptr, out_scores, out_idx, stream);
+  return launch_merge(static_cast<const float*>(records), nullptr, g, q, k, nullptr, out_scores, out_idx, stream);
 }
 
 }  // extern "C"

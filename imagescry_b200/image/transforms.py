@@ -6,7 +6,8 @@ Same names, signatures, argument meaning and error behaviour as the reference mo
 CUDA device; there is no CPU path.
 
 Beyond the reference's surface, `preprocess_tiles` exposes the fused stage-1 pipeline directly
-(optional NHWC uint8 input, resize folded into both passes, fp32 or bf16 output).
+(optional NHWC uint8 input, resize folded into both passes, fp32 or bf16 output) and
+`preprocess_patches` adds patch tiling of large images as index arithmetic inside the same passes.
 """
 
 from __future__ import annotations
@@ -39,10 +40,11 @@ def _stats(x: Tensor, layout: int, B: int, C: int, H: int, W: int, oh: int, ow: 
     std = torch.empty(C, dtype=torch.float32, device=x.device)
     ws_bytes = lib.isx_preprocess_stats_workspace_bytes(C)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    rc = lib.isx_preprocess_stats(
-        x.data_ptr(), _IN_DTYPES[x.dtype], layout, B, C, H, W, oh, ow, mean.data_ptr(), std.data_ptr(),
-        ws.data_ptr(), ws_bytes, _lib.stream_ptr(x.device),
-    )
+    with _lib.on_device(x) as stream:
+        rc = lib.isx_preprocess_stats(
+            x.data_ptr(), _IN_DTYPES[x.dtype], layout, B, C, H, W, oh, ow, mean.data_ptr(), std.data_ptr(),
+            ws.data_ptr(), ws_bytes, stream,
+        )
     _lib.check(rc, "isx_preprocess_stats")
     return mean, std
 
@@ -53,11 +55,12 @@ def _apply(
 ) -> Tensor:
     lib = _lib.load()
     out = torch.empty((B, C, oh, ow), dtype=out_dtype, device=x.device)
-    rc = lib.isx_preprocess_apply(
-        x.data_ptr(), _IN_DTYPES[x.dtype], layout, B, C, H, W, oh, ow, mean.data_ptr(), std.data_ptr(), stat_batch,
-        float(eps), int(min_value is not None), float(min_value or 0.0), int(max_value is not None),
-        float(max_value or 0.0), out.data_ptr(), _OUT_DTYPES[out_dtype], _lib.stream_ptr(x.device),
-    )
+    with _lib.on_device(x, mean, std) as stream:
+        rc = lib.isx_preprocess_apply(
+            x.data_ptr(), _IN_DTYPES[x.dtype], layout, B, C, H, W, oh, ow, mean.data_ptr(), std.data_ptr(), stat_batch,
+            float(eps), int(min_value is not None), float(min_value or 0.0), int(max_value is not None),
+            float(max_value or 0.0), out.data_ptr(), _OUT_DTYPES[out_dtype], stream,
+        )
     _lib.check(rc, "isx_preprocess_apply")
     return out
 
@@ -120,6 +123,88 @@ def preprocess_tiles(
     return _apply(x, lay, B, C, H, W, oh, ow, mean, std, sb, eps, min_value, max_value, out_dtype)
 
 
+def patch_grid(height: int, width: int, patch_size: int, stride: int | None = None) -> tuple[int, int]:
+    """(ny, nx): full `patch_size` windows on a `stride` grid that fit an image of height x width."""
+    stride = patch_size if stride is None else stride
+    if patch_size < 1 or stride < 1:
+        raise ValueError(f"patch_size and stride must be positive, got {patch_size} and {stride}")
+    if patch_size > height or patch_size > width:
+        raise ValueError(f"patch_size {patch_size} exceeds the image size {height}x{width}")
+    return (height - patch_size) // stride + 1, (width - patch_size) // stride + 1
+
+
+def preprocess_patches(
+    images: Tensor,
+    patch_size: int,
+    *,
+    stride: int | None = None,
+    layout: Literal["nchw", "nhwc"] = "nhwc",
+    output_hw: tuple[int, int] | None = None,
+    channel_means: Tensor | None = None,
+    channel_stds: Tensor | None = None,
+    min_value: float | None = None,
+    max_value: float | None = None,
+    eps: float = 1e-6,
+    out_dtype: torch.dtype = torch.float32,
+) -> Tensor:
+    """Patch tiling fused into stage 1: cut uint8 3-channel images (`n×H×W×3` or `n×3×H×W`) into
+    `patch_size` windows on a `stride` grid (full windows only, ordered image, py, px) and preprocess
+    the windows as a tile batch — `preprocess_tiles` on a patch tensor that is never built: the
+    window offsets are index arithmetic inside the statistics and apply kernels' reads.
+
+    Returns `(n·ny·nx)×3×outH×outW`.  The reference has no patch tiling; the
+    semantics are the oracle's `preprocess_patches` restatement."""
+    _lib.require_cuda(images, "images")
+    if images.ndim != 4 or images.dtype != torch.uint8:
+        raise ValueError(f"images must be a 4-D uint8 tensor, got {images.dtype} with shape {tuple(images.shape)}")
+    x = images.contiguous()
+    if layout == "nhwc":
+        n, H, W, C = x.shape
+        lay = _lib.LAYOUT_NHWC
+    elif layout == "nchw":
+        n, C, H, W = x.shape
+        lay = _lib.LAYOUT_NCHW
+    else:
+        raise ValueError(f"Invalid layout: {layout}")
+    if C != 3:
+        raise ValueError(f"patch tiling supports 3-channel images, got {C} channels")
+    stride = patch_size if stride is None else int(stride)
+    ny, nx = patch_grid(H, W, patch_size, stride)
+    oh, ow = (patch_size, patch_size) if output_hw is None else (int(output_hw[0]), int(output_hw[1]))
+    if out_dtype not in _OUT_DTYPES:
+        raise ValueError(f"out_dtype must be float32 or bfloat16, got {out_dtype}")
+    B = n * ny * nx
+    out = torch.empty((B, 3, oh, ow), dtype=out_dtype, device=x.device)
+    if B == 0:
+        return out
+    lib = _lib.load()
+    if channel_means is None or channel_stds is None:
+        mean = torch.empty(3, dtype=torch.float32, device=x.device)
+        std = torch.empty(3, dtype=torch.float32, device=x.device)
+        ws_bytes = lib.isx_preprocess_stats_workspace_bytes(3)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        with _lib.on_device(x) as stream:
+            rc = lib.isx_preprocess_patches_stats(
+                x.data_ptr(), lay, n, 3, H, W, patch_size, stride, oh, ow, mean.data_ptr(), std.data_ptr(), ws.data_ptr(),
+                ws_bytes, stream,
+            )
+        _lib.check(rc, "isx_preprocess_patches_stats")
+    if channel_means is not None:
+        mean = channel_means.to(device=x.device, dtype=torch.float32).reshape(-1).contiguous()
+    if channel_stds is not None:
+        std = channel_stds.to(device=x.device, dtype=torch.float32).reshape(-1).contiguous()
+    if mean.numel() != 3 or std.numel() != 3:
+        raise ValueError("patch tiling takes batch-wide statistics: channel_means / channel_stds must hold 3 values")
+    with _lib.on_device(x, mean, std) as stream:
+        rc = lib.isx_preprocess_patches_apply(
+            x.data_ptr(), lay, n, 3, H, W, patch_size, stride, oh, ow, mean.data_ptr(), std.data_ptr(), float(eps),
+            int(min_value is not None), float(min_value or 0.0), int(max_value is not None), float(max_value or 0.0),
+            out.data_ptr(), _OUT_DTYPES[out_dtype], stream,
+        )
+    _lib.check(rc, "isx_preprocess_patches_apply")
+    return out
+
+
 @jaxtyped(typechecker=typechecker)
 def normalize_per_channel(
     image_tensor: Num[Tensor, "B C H W"],
@@ -157,10 +242,10 @@ def resize(
     out = torch.empty((B, C, oh, ow), dtype=torch.float32, device=x.device)
     if out.numel() > 0:
         lib = _lib.load()
-        rc = lib.isx_resize_bilinear(
-            x.data_ptr(), _IN_DTYPES[x.dtype], _lib.LAYOUT_NCHW, B, C, H, W, oh, ow, out.data_ptr(),
-            _lib.stream_ptr(x.device),
-        )
+        with _lib.on_device(x) as stream:
+            rc = lib.isx_resize_bilinear(
+                x.data_ptr(), _IN_DTYPES[x.dtype], _lib.LAYOUT_NCHW, B, C, H, W, oh, ow, out.data_ptr(), stream
+            )
         _lib.check(rc, "isx_resize_bilinear")
     return out.squeeze(squeeze_dims) if squeeze_dims else out
 

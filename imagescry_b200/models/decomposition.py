@@ -3,7 +3,7 @@
 `PCA.forward` / `PCA.transform` (`decomposition.py:79-91,150-165`) run the fused sm_100a projection
 kernel (`isx_l2norm_project` with `normalize=0`); `project_feature_map` exposes the fully fused
 L2-normalise (+pool) + projection of a backbone feature map.  `fit` (`:94-148`) takes its means
-and covariance from the sm_100a moment kernels (`isx_pca_moments`) for CUDA input.
+and covariance from the sm_100a moment kernels (`isx_pca_moments`, a tcgen05 SYRK).
 
 The reference derives from `LightningModule`; lightning is not part of this image, so the base is
 `torch.nn.Module` with the same hyper-parameter surface (`hparams`, `save_hyperparameters`).
@@ -43,6 +43,19 @@ class HParamsModule(nn.Module):
         return self._hparams
 
 
+def select_num_components(
+    explained_variance: Tensor, min_num_components: int, max_num_components: int | None, min_explained_variance: float
+) -> int:
+    """The reference's selection rule (`decomposition.py:128-137`): the fewest components whose
+    cumulative explained variance reaches `min_explained_variance`, clamped to [min, max]."""
+    cumulative = torch.cumsum(explained_variance, dim=0)
+    need = int(torch.sum(cumulative < min_explained_variance).item() + 1)
+    num_components = max(min_num_components, need)
+    if max_num_components is not None:
+        num_components = min(max_num_components, num_components)
+    return num_components
+
+
 class PCA(HParamsModule):
     """Principal component analysis: linear projection to a lower dimensional space via SVD."""
 
@@ -78,8 +91,23 @@ class PCA(HParamsModule):
         self.feature_means = nn.Parameter(torch.empty((1, num_features)), requires_grad=False)
         self.explained_variance = nn.Parameter(torch.empty((num_features,)), requires_grad=False)
         self.component_vectors = nn.Parameter(torch.empty((num_features, num_components)), requires_grad=False)
-        self._packed: Tensor | None = None
-        self._packed_key: tuple | None = None
+        self.__dict__["_packed"] = None
+        self.__dict__["_packed_key"] = None
+        self.__dict__["_fitted_key"] = None
+
+    def __setattr__(self, name: str, value) -> None:
+        # re-assigned weights invalidate the packed operand (a new tensor may reuse a freed address)
+        if name in ("component_vectors", "feature_means", "_fitted"):
+            self.__dict__["_packed"] = None
+            self.__dict__["_packed_key"] = None
+            self.__dict__["_fitted_key"] = None
+        super().__setattr__(name, value)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.__dict__["_packed"] = None
+        self.__dict__["_packed_key"] = None
+        self.__dict__["_fitted_key"] = None
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def __repr__(self) -> str:
         num_features = self.num_features if self.fitted else "not fitted"
@@ -115,10 +143,11 @@ class PCA(HParamsModule):
             packed = torch.empty(nbytes, dtype=torch.uint8, device=cv.device)
             means = fm.detach().reshape(-1).contiguous().float()
             comps = cv.detach().float()
-            rc = lib.isx_project_pack(
-                means.data_ptr(), comps.data_ptr(), F, k, comps.stride(0), comps.stride(1), packed.data_ptr(), nbytes,
-                _lib.stream_ptr(cv.device),
-            )
+            with _lib.on_device(means, comps) as stream:
+                rc = lib.isx_project_pack(
+                    means.data_ptr(), comps.data_ptr(), F, k, comps.stride(0), comps.stride(1), packed.data_ptr(),
+                    nbytes, stream,
+                )
             _lib.check(rc, "isx_project_pack")
             self._packed, self._packed_key = packed, key
         return self._packed
@@ -137,10 +166,9 @@ class PCA(HParamsModule):
             return out
         xf = x.float().contiguous()
         lib = _lib.load()
-        rc = lib.isx_l2norm_project(
-            xf.data_ptr(), n, F, 1, 1, 0, 0, self.packed_weights().data_ptr(), k, out.data_ptr(), None, 0,
-            _lib.stream_ptr(x.device),
-        )
+        packed = self.packed_weights()
+        with _lib.on_device(xf, packed) as stream:
+            rc = lib.isx_l2norm_project(xf.data_ptr(), n, F, 1, 1, 0, 0, packed.data_ptr(), k, out.data_ptr(), None, 0, stream)
         _lib.check(rc, "isx_l2norm_project")
         return out
 
@@ -186,10 +214,12 @@ class PCA(HParamsModule):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=f.device)
         if B > 0:
             entry = lib.isx_l2norm_project if precision == "exact" else lib.isx_l2norm_project_fp16
-            rc = entry(
-                f.data_ptr(), B, E, h, w, int(pool is not None), 1, self.packed_weights().data_ptr(), k,
-                out.data_ptr(), None if ws is None else ws.data_ptr(), ws_bytes, _lib.stream_ptr(f.device),
-            )
+            packed = self.packed_weights()
+            with _lib.on_device(f, packed) as stream:
+                rc = entry(
+                    f.data_ptr(), B, E, h, w, int(pool is not None), 1, packed.data_ptr(), k,
+                    out.data_ptr(), None if ws is None else ws.data_ptr(), ws_bytes, stream,
+                )
             _lib.check(rc, "isx_l2norm_project")
         return out.permute(0, 3, 1, 2) if pool is None else out
 
@@ -203,9 +233,8 @@ class PCA(HParamsModule):
         cov = torch.empty((F, F), dtype=torch.float32, device=xf.device)
         ws_bytes = int(lib.isx_pca_moments_workspace_bytes(n, F))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xf.device)
-        rc = lib.isx_pca_moments(
-            xf.data_ptr(), n, F, mean.data_ptr(), cov.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(xf.device)
-        )
+        with _lib.on_device(xf) as stream:
+            rc = lib.isx_pca_moments(xf.data_ptr(), n, F, mean.data_ptr(), cov.data_ptr(), ws.data_ptr(), ws_bytes, stream)
         _lib.check(rc, "isx_pca_moments")
         return mean, cov
 
@@ -214,42 +243,36 @@ class PCA(HParamsModule):
         """Fit (`decomposition.py:94-148`): same component-selection rule (min/max components,
         minimum explained variance) and the same fitted tensors as the reference.
 
-        CUDA input: means and the F×F covariance come from the sm_100a moment kernels (one pass each
-        over x); its eigen-pairs are the reference's `vt` rows and `s²/(n-1)` (:122-125) without the
-        full SVD's n×n `U`.  Signs of the component vectors are as arbitrary as the reference's own.
-        CPU input (offline use, tests): the reference's algorithm on torch."""
+        Means and the F×F covariance of the fp32-centred data come from the sm_100a moment kernels
+        (`isx_pca_moments`: fp64 column means, tcgen05 SYRK with a bf16 hi/lo split); the covariance's
+        eigen-pairs are the reference's `vt` rows and `s²/(n-1)` (:122-125) without the full SVD's n×n
+        `U`.  The F×F `eigh` (fp64) is a small dense library call.  Signs of the component vectors
+        are as arbitrary as the reference's own.  CUDA tensors only: there is no CPU path.
+
+        Numerical note: eigenvalues come from the covariance (condition number squared relative to
+        the SVD of the data), so explained-variance ratios below ~1e-7 of the total are noise; the
+        reference's SVD resolves ~1e-14.  Component selection differs only if `min_explained_variance`
+        falls within that distance of a cumulative-variance step."""
+        _lib.require_cuda(x, "x")
         num_samples, num_features = x.shape
         if num_samples < 2:
             raise ValueError(f"num_samples must be at least 2, got {num_samples}")
         self._num_features = nn.Parameter(torch.tensor(num_features), requires_grad=False)
-        if x.is_cuda:
-            mean, cov = self._moments(x)
-            self.feature_means = nn.Parameter(mean.reshape(1, -1), requires_grad=False)
-            evals, evecs = torch.linalg.eigh(cov.double())  # ascending; 6.5 MB problem at F = 1280
-            eigenvalues = evals.flip(0).clamp_min(0.0).float()
-            vt = evecs.flip(1).T.float()  # rows = principal directions, like the SVD's vt
-        else:
-            self.feature_means = nn.Parameter(x.mean(dim=0, keepdim=True), requires_grad=False)
-            x_centered = x - self.feature_means
-            # Only the singular values and right singular vectors are used; the reduced SVD yields
-            # the same `s` and `vt` as the reference's full one without the num_samples² `U`.
-            _, s, vt = torch.linalg.svd(x_centered, full_matrices=False)
-            if vt.shape[0] < num_features:  # fewer samples than features: pad like the full SVD's shapes
-                s = torch.cat([s, s.new_zeros(num_features - s.shape[0])])
-            eigenvalues = s**2 / (num_samples - 1)
+        mean, cov = self._moments(x)
+        self.feature_means = nn.Parameter(mean.reshape(1, -1), requires_grad=False)
+        evals, evecs = torch.linalg.eigh(cov.double())  # ascending; 6.5 MB problem at F = 1280
+        rank = min(num_samples, num_features)  # the SVD's `s` has min(n, F) entries (:122-125)
+        eigenvalues = evals.flip(0).clamp_min(0.0).float()[:rank]
+        vt = evecs.flip(1).T.float()  # rows = principal directions, like the SVD's vt
         total_variance = torch.sum(eigenvalues)
         self.explained_variance = nn.Parameter(eigenvalues / total_variance, requires_grad=False)
-        cumulative = torch.cumsum(self.explained_variance, dim=0)
-        need = int(torch.sum(cumulative < self.min_explained_variance).item() + 1)
-        num_components = max(self.min_num_components, need)
-        if self.max_num_components is not None:
-            num_components = min(self.max_num_components, num_components)
-        num_components = min(num_components, vt.shape[0])
+        num_components = select_num_components(
+            self.explained_variance, self.min_num_components, self.max_num_components, self.min_explained_variance
+        )
         self._num_components = nn.Parameter(torch.tensor(num_components), requires_grad=False)
         self.component_vectors = nn.Parameter(vt[:num_components, :].T, requires_grad=False)
         self._fitted = nn.Parameter(torch.tensor(True), requires_grad=False)
         self.hparams.update({"num_features": num_features, "num_components": num_components})
-        self._packed = None
         return self
 
     @jaxtyped(typechecker=typechecker)

@@ -4,8 +4,8 @@
 `preprocess` and `forward`; `predict_step` chains preprocess → forward → per-cell L2 normalisation.
 `EfficientNetEmbedder.preprocess` (`:150-165`) is the fused CUDA stage 1.  The backbone's `forward`
 (`:168-177`) stays torchvision's EfficientNetV2 `.features` — reported, not owned.
-The per-cell L2 step of `predict_step` (`:74`) is library code here (`F.normalize`, as in the
-reference); the pipeline (`models/pipelines.py`) fuses it into the projection kernel instead.
+The per-cell L2 step of `predict_step` (`:74`) is the one-pass `isx_l2norm_cells` kernel; the
+pipeline (`models/pipelines.py`) fuses it into the projection kernel instead.
 """
 
 from __future__ import annotations
@@ -17,10 +17,27 @@ import torch
 from jaxtyping import Float, UInt8, jaxtyped
 from torch import Tensor, nn
 
+from imagescry_b200 import _lib
 from imagescry_b200.data import EmbeddingBatch, ImageBatch
-from imagescry_b200.image.transforms import preprocess_tiles, resized_shape
+from imagescry_b200.image.transforms import preprocess_patches, preprocess_tiles, resized_shape
 from imagescry_b200.models.decomposition import HParamsModule
 from imagescry_b200.typechecking import typechecker
+
+
+def l2_normalize_cells(fmap: Tensor, eps: float = 1e-12) -> Tensor:
+    """`nn.functional.normalize(x, p=2, dim=1)` of a B×E×h×w feature map (`embedding.py:74`): every
+    spatial cell divided by `max(||cell||_2, eps)` over the channels, in one pass over HBM."""
+    _lib.require_cuda(fmap, "fmap")
+    if fmap.ndim != 4:
+        raise ValueError(f"fmap must be B×E×h×w, got shape {tuple(fmap.shape)}")
+    x = fmap.float().contiguous()
+    out = torch.empty_like(x)
+    B, E, h, w = x.shape
+    if x.numel():
+        with _lib.on_device(x) as stream:
+            rc = _lib.load().isx_l2norm_cells(x.data_ptr(), B, E, h, w, float(eps), out.data_ptr(), stream)
+        _lib.check(rc, "isx_l2norm_cells")
+    return out
 
 
 class EmbeddingModule(ABC, HParamsModule):
@@ -42,7 +59,7 @@ class EmbeddingModule(ABC, HParamsModule):
     def predict_step(self, batch: ImageBatch) -> EmbeddingBatch:
         """Preprocess, extract the feature map, L2-normalise each cell (`embedding.py:57-76`)."""
         x = self.feature_map(batch)
-        x = nn.functional.normalize(x, p=2, dim=1)
+        x = l2_normalize_cells(x)
         return EmbeddingBatch(indices=batch.indices, embeddings=x)
 
     def embed_images(self, dataloader) -> list[EmbeddingBatch]:
@@ -106,6 +123,20 @@ class EfficientNetEmbedder(EmbeddingModule):
         out_hw = resized_shape(h, w, self.max_side_length, "long") if max(h, w) > self.max_side_length else None
         return preprocess_tiles(
             tiles, layout="nhwc", output_hw=out_hw, min_value=-3, max_value=3, out_dtype=self.preprocess_dtype
+        )
+
+    def preprocess_patches(
+        self, images: UInt8[Tensor, "n H W C"], patch_size: int, *, stride: int | None = None, layout: str = "nhwc"
+    ) -> Tensor:
+        """Patch tiling + `preprocess` in one fused pass pair: large HWC images are cut into
+        `patch_size` windows (stride defaults to the patch size) and every window is treated as a tile
+        (resized iff larger than `max_side_length`, normalised with batch statistics, clipped)."""
+        out_hw = (
+            resized_shape(patch_size, patch_size, self.max_side_length, "long") if patch_size > self.max_side_length else None
+        )
+        return preprocess_patches(
+            images, patch_size, stride=stride, layout=layout, output_hw=out_hw, min_value=-3, max_value=3,
+            out_dtype=self.preprocess_dtype,
         )
 
     @jaxtyped(typechecker=typechecker)

@@ -40,7 +40,8 @@ def row_rnorm(x: Tensor, eps: float = 1e-12) -> Tensor:
     n, d = x.shape
     out = torch.empty(n, dtype=torch.float32, device=x.device)
     if n:
-        rc = _lib.load().isx_row_rnorm_bf16(x.data_ptr(), n, d, eps, out.data_ptr(), _lib.stream_ptr(x.device))
+        with _lib.on_device(x) as stream:
+            rc = _lib.load().isx_row_rnorm_bf16(x.data_ptr(), n, d, eps, out.data_ptr(), stream)
         _lib.check(rc, "isx_row_rnorm_bf16")
     return out
 
@@ -60,19 +61,61 @@ def merge_topk(scores: Tensor, indices: Tensor, k: int | None = None) -> tuple[T
     out_s = torch.empty((q, k), dtype=torch.float32, device=s.device)
     out_i = torch.empty((q, k), dtype=torch.int32, device=s.device)
     if q:
-        rc = _lib.load().isx_topk_merge(
-            s.data_ptr(), i.data_ptr(), g, q, k, out_s.data_ptr(), out_i.data_ptr(), _lib.stream_ptr(s.device)
-        )
+        with _lib.on_device(s, i) as stream:
+            rc = _lib.load().isx_topk_merge(s.data_ptr(), i.data_ptr(), g, q, k, out_s.data_ptr(), out_i.data_ptr(), stream)
         _lib.check(rc, "isx_topk_merge")
     return out_s, out_i
 
 
+def merge_topk_packed(records: Tensor, k: int | None = None) -> tuple[Tensor, Tensor]:
+    """Merge G partial results held as packed records (G×Q×k int64: low word = fp32 score bits, high
+    word = int32 index, what `EmbeddingStore.search_packed` writes and ONE all-gather moves) into
+    (scores fp32 Q×k, indices int32 Q×k), ordered by (score desc, index asc)."""
+    _lib.require_cuda(records, "records")
+    if records.ndim != 3 or records.dtype != torch.int64:
+        raise ValueError("records must be a G×Q×k int64 tensor")
+    g, q, kk = records.shape
+    k = kk if k is None else k
+    if k != kk:
+        raise ValueError(f"k={k} does not match the partial lists' width {kk}")
+    r = records.contiguous()
+    out_s = torch.empty((q, k), dtype=torch.float32, device=r.device)
+    out_i = torch.empty((q, k), dtype=torch.int32, device=r.device)
+    if q:
+        with _lib.on_device(r) as stream:
+            rc = _lib.load().isx_topk_merge_packed(r.data_ptr(), g, q, k, out_s.data_ptr(), out_i.data_ptr(), stream)
+        _lib.check(rc, "isx_topk_merge_packed")
+    return out_s, out_i
+
+
+def pack_records(scores: Tensor, indices: Tensor) -> Tensor:
+    """(fp32 score, int32 index) → int64 records, little-endian {score bits, index} like the kernel's
+    8-byte records (host-side helper for tests and CPU plumbing; not on the search path)."""
+    words = torch.stack([scores.contiguous().float().view(torch.int32), indices.to(torch.int32)], dim=-1)
+    return words.contiguous().view(torch.int64).squeeze(-1)
+
+
+def unpack_records(records: Tensor) -> tuple[Tensor, Tensor]:
+    """int64 records → (fp32 scores, int32 indices); inverse of `pack_records`."""
+    words = records.contiguous().view(torch.int32).view(*records.shape, 2)
+    return words[..., 0].contiguous().view(torch.float32), words[..., 1].contiguous()
+
+
 def _as_bf16_matrix(x: Tensor, name: str) -> Tensor:
+    """bf16, contiguous, and — the kernel's TMA rows are 16-byte units — zero-padded to a multiple of
+    8 features.  Zero features change neither dot products nor norms, so cosine scores are unchanged
+    (the reference's PCA picks `num_components` from `min_explained_variance`: widths like 37 are
+    normal, `decomposition.py:128-137`)."""
     _lib.require_cuda(x, name)
     if x.ndim != 2:
         raise ValueError(f"{name} must be 2-D (rows × features), got shape {tuple(x.shape)}")
     if not x.dtype.is_floating_point:
         raise ValueError(f"{name} must be a floating-point tensor, got {x.dtype}")
+    d = x.shape[1]
+    if d % 8:
+        out = torch.zeros((x.shape[0], (d + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)
+        out[:, :d] = x
+        return out
     return x.to(torch.bfloat16).contiguous()
 
 
@@ -80,19 +123,26 @@ class EmbeddingStore:
     """A device-resident N×d bf16 embedding matrix with its inverse row norms.
 
     Vectors are kept as given (not re-rounded after normalisation): the kernel multiplies bf16×bf16
-    products exactly, accumulates in fp32 and applies both inverse norms in the epilogue."""
+    products exactly, accumulates in fp32 and applies both inverse norms in the epilogue.
+
+    A store may be searched from several CUDA streams: the scratch workspace (running top-k lists,
+    per-query locks and bounds) is cached per stream."""
 
     def __init__(self, embeddings: Tensor, *, index_base: int = 0) -> None:
+        if embeddings.ndim != 2:
+            raise ValueError(f"embeddings must be 2-D (rows × features), got shape {tuple(embeddings.shape)}")
+        self.num_features = embeddings.shape[1]
         self.embeddings = _as_bf16_matrix(embeddings, "embeddings")
         self.index_base = int(index_base)
         self.rnorm = row_rnorm(self.embeddings)
-        self._workspace: Tensor | None = None
+        self._workspaces: dict[int, Tensor] = {}
 
     def __len__(self) -> int:
         return self.embeddings.shape[0]
 
     @property
     def dim(self) -> int:
+        """Row width in memory (`num_features` rounded up to a multiple of 8)."""
         return self.embeddings.shape[1]
 
     @property
@@ -100,72 +150,96 @@ class EmbeddingStore:
         return self.embeddings.device
 
     def _ws(self, nbytes: int) -> Tensor:
-        if self._workspace is None or self._workspace.numel() < nbytes:
-            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        return self._workspace
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._workspaces.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._workspaces[key] = ws
+        return ws
+
+    def _queries(self, queries: Tensor) -> Tensor:
+        if queries.ndim != 2:
+            raise ValueError(f"queries must be 2-D (rows × features), got shape {tuple(queries.shape)}")
+        if queries.shape[1] != self.num_features and queries.shape[1] != self.dim:
+            raise ValueError(f"queries have {queries.shape[1]} features, the store has {self.num_features}")
+        q = _as_bf16_matrix(queries, "queries")
+        if q.device != self.device:
+            raise ValueError(f"queries are on {q.device}, the store is on {self.device}")
+        return q
+
+    def search_block(
+        self, rows: Tensor, rows_rnorm: Tensor, index_base: int, q: Tensor, q_rnorm: Tensor, k: int, *, flags: int = 0,
+        query_index_base: int = 0, out_a: Tensor | None = None, out_b: Tensor | None = None,
+    ) -> None:
+        """One `isx_knn_search_ex` call: search the bf16 block `rows` (global indices from `index_base`)
+        for the prepared queries `q`, on this store's per-stream workspace.  With `KNN_CONTINUE` the
+        block is added to the running lists of the previous call (same q and k)."""
+        lib = _lib.load()
+        nq = q.shape[0]
+        ws_bytes = max(int(lib.isx_knn_workspace_bytes(max(rows.shape[0], 1), nq, q.shape[1], k)), 256)
+        ws = self._ws(ws_bytes)
+        with _lib.on_device(rows, rows_rnorm, q, q_rnorm, out_a, out_b, ws) as stream:
+            rc = lib.isx_knn_search_ex(
+                rows.data_ptr(), rows_rnorm.data_ptr(), rows.shape[0], q.data_ptr(), q_rnorm.data_ptr(), nq, q.shape[1], k,
+                int(index_base), int(query_index_base), int(flags), None if out_a is None else out_a.data_ptr(),
+                None if out_b is None else out_b.data_ptr(), ws.data_ptr(), ws.numel(), stream,
+            )
+        _lib.check(rc, "isx_knn_search_ex")
+
+    def _check_k(self, k: int) -> None:
+        if not (1 <= k <= MAX_K):
+            raise ValueError(f"k must be between 1 and {MAX_K}, got {k}")
 
     def search_raw(self, queries: Tensor, k: int, *, query_rnorm: Tensor | None = None) -> tuple[Tensor, Tensor]:
         """Local top-k: fp32 scores Q×k and int32 global indices Q×k (padding: -inf / -1)."""
-        q = _as_bf16_matrix(queries, "queries")
-        if q.shape[1] != self.dim:
-            raise ValueError(f"queries have {q.shape[1]} features, the store has {self.dim}")
-        if not (1 <= k <= MAX_K):
-            raise ValueError(f"k must be between 1 and {MAX_K}, got {k}")
-        if q.device != self.device:
-            raise ValueError(f"queries are on {q.device}, the store is on {self.device}")
+        q = self._queries(queries)
+        self._check_k(k)
         nq = q.shape[0]
         scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
         idx = torch.empty((nq, k), dtype=torch.int32, device=self.device)
         if nq == 0:
             return scores, idx
         qr = row_rnorm(q) if query_rnorm is None else query_rnorm
-        lib = _lib.load()
-        n = len(self)
-        ws_bytes = max(int(lib.isx_knn_workspace_bytes(n, nq, self.dim, k)), 256)
-        ws = self._ws(ws_bytes)
-        rc = lib.isx_knn_search(
-            self.embeddings.data_ptr(), self.rnorm.data_ptr(), n, q.data_ptr(), qr.data_ptr(), nq, self.dim, k,
-            self.index_base, scores.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(),
-            _lib.stream_ptr(self.device),
-        )
-        _lib.check(rc, "isx_knn_search")
+        self.search_block(self.embeddings, self.rnorm, self.index_base, q, qr, k, out_a=scores, out_b=idx)
         return scores, idx
+
+    def search_packed(self, queries: Tensor, k: int, *, query_rnorm: Tensor | None = None, out: Tensor | None = None) -> Tensor:
+        """Local top-k as Q×k packed int64 records {fp32 score, int32 global index}: the form a
+        row-sharded search all-gathers in ONE collective (`merge_topk_packed` consumes it)."""
+        q = self._queries(queries)
+        self._check_k(k)
+        nq = q.shape[0]
+        rec = torch.empty((nq, k), dtype=torch.int64, device=self.device) if out is None else out
+        if nq == 0:
+            return rec
+        qr = row_rnorm(q) if query_rnorm is None else query_rnorm
+        self.search_block(self.embeddings, self.rnorm, self.index_base, q, qr, k, flags=_lib.KNN_PACKED, out_a=rec)
+        return rec
 
     def search(self, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
         """Cosine top-k of every query row: (scores fp32 Q×k, indices int64 Q×k)."""
         scores, idx = self.search_raw(queries, k)
         return scores, idx.to(torch.int64)
 
+    def knn_graph(self, k: int) -> tuple[Tensor, Tensor]:
+        """All-pairs similarity graph (BASELINE.json config 5): the k nearest OTHER rows of every row,
+        (scores N×k fp32, indices N×k int64).  One fused search with the store's own rows as queries;
+        a row's own entry is skipped inside the kernel's selection (no k + 1 search, no post-filter)."""
+        self._check_k(k)
+        n = len(self)
+        scores = torch.empty((n, k), dtype=torch.float32, device=self.device)
+        idx = torch.empty((n, k), dtype=torch.int32, device=self.device)
+        if n:
+            self.search_block(
+                self.embeddings, self.rnorm, self.index_base, self.embeddings, self.rnorm, k,
+                flags=_lib.KNN_EXCLUDE_SELF, query_index_base=self.index_base, out_a=scores, out_b=idx,
+            )
+        return scores, idx.to(torch.int64)
 
-def drop_self_matches(scores: Tensor, indices: Tensor, query_rows: Tensor, k: int) -> tuple[Tensor, Tensor]:
-    """From Q×(k+1) results whose queries are store rows `query_rows` (global indices), remove each
-    query's own row and keep the first k of the rest (order preserved).  If the row itself is not
-    among the k+1 hits (k+1 exact duplicates with lower indices), the last hit is dropped."""
-    q, k1 = indices.shape
-    if k1 != k + 1:
-        raise ValueError(f"expected k + 1 = {k + 1} columns, got {k1}")
-    is_self = indices == query_rows.to(indices.dtype).reshape(-1, 1)
-    # position of the column to drop: the self hit, else the last column
-    drop = torch.where(is_self.any(dim=1), is_self.to(torch.int8).argmax(dim=1), torch.full((q,), k, device=indices.device))
-    cols = torch.arange(k, device=indices.device).reshape(1, -1)
-    take = cols + (cols >= drop.reshape(-1, 1)).to(cols.dtype)
-    return scores.gather(1, take), indices.gather(1, take)
 
-
-def knn_graph(store: "EmbeddingStore", k: int, *, block: int = 131072) -> tuple[Tensor, Tensor]:
-    """All-pairs similarity graph over a store (BASELINE.json config 5): the k nearest other rows of
-    every row.  Queries are the store's own rows, searched in blocks with k + 1 and the self match
-    removed.  Returns (scores N×k fp32, indices N×k int64)."""
-    n = len(store)
-    out_s = torch.empty((n, k), dtype=torch.float32, device=store.device)
-    out_i = torch.empty((n, k), dtype=torch.int64, device=store.device)
-    for b in range(0, n, block):
-        e = min(n, b + block)
-        s, i = store.search_raw(store.embeddings[b:e], k + 1, query_rnorm=store.rnorm[b:e])
-        rows = torch.arange(b, e, device=store.device) + store.index_base
-        s, i = drop_self_matches(s, i.to(torch.int64), rows, k)
-        out_s[b:e], out_i[b:e] = s, i
-    return out_s, out_i
+def knn_graph(store: "EmbeddingStore", k: int) -> tuple[Tensor, Tensor]:
+    """All-pairs similarity graph over a store: see `EmbeddingStore.knn_graph`."""
+    return store.knn_graph(k)
 
 
 def knn_search(embeddings: Tensor, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
@@ -173,19 +247,41 @@ def knn_search(embeddings: Tensor, queries: Tensor, k: int) -> tuple[Tensor, Ten
     return EmbeddingStore(embeddings).search(queries, k)
 
 
+def gather_records(records: Tensor, group=None) -> Tensor:
+    """All-gather every rank's packed local top-k (Q×k int64): returns G×Q×k.  The ONE collective of
+    a sharded search; backend-agnostic (NCCL over NVLink on GPUs, gloo in CPU tests)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    q, k = records.shape
+    # concatenation along dim 0 is the one output form every backend (NCCL, gloo) accepts
+    out = torch.empty((world * q, k), dtype=records.dtype, device=records.device)
+    dist.all_gather_into_tensor(out, records.contiguous(), group=group)
+    return out.view(world, q, k)
+
+
 def gather_partials(scores: Tensor, idx: Tensor, group=None) -> tuple[Tensor, Tensor]:
-    """All-gather every rank's local top-k: returns (G×Q×k scores, G×Q×k indices).  The only
-    collective of the sift path; backend-agnostic (NCCL over NVLink on GPUs, gloo in CPU tests)."""
+    """Two-array form of `gather_records` (kept for callers that hold separate score / index
+    tensors): returns (G×Q×k scores, G×Q×k indices)."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     q, k = scores.shape
-    # concatenation along dim 0 is the one output form every backend (NCCL, gloo) accepts
     all_s = torch.empty((world * q, k), dtype=scores.dtype, device=scores.device)
     all_i = torch.empty((world * q, k), dtype=idx.dtype, device=idx.device)
     dist.all_gather_into_tensor(all_s, scores.contiguous(), group=group)
     dist.all_gather_into_tensor(all_i, idx.contiguous(), group=group)
     return all_s.view(world, q, k), all_i.view(world, q, k)
+
+
+def graph_chunk_plan(sizes: list[int], dim: int, budget_bytes: int) -> tuple[int, int]:
+    """Chunking of the store rotation in `ShardedEmbeddingStore.knn_graph`: every step all-gathers
+    rows [c, c + chunk) of every rank's shard.  Returns (chunk rows per rank, number of steps) such
+    that the gathered buffer (world × chunk × dim bf16) stays within `budget_bytes`."""
+    per = max(sizes)
+    world = len(sizes)
+    chunk = max(1, min(per, budget_bytes // max(1, world * dim * 2)))
+    return chunk, (per + chunk - 1) // chunk if per else 0
 
 
 class ShardedEmbeddingStore:
@@ -212,51 +308,88 @@ class ShardedEmbeddingStore:
         self.total_rows = total_rows
         self.local = EmbeddingStore(local_embeddings, index_base=index_base)
 
+    def search_raw(self, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
+        """(scores fp32 Q×k, GLOBAL indices int32 Q×k): local fused search → ONE all-gather of packed
+        (score, index) records → merge."""
+        rec = self.local.search_packed(queries, k)
+        return merge_topk_packed(gather_records(rec, self.group), k)
+
     def search(self, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
-        scores, idx = self.local.search_raw(queries, k)
-        all_s, all_i = gather_partials(scores, idx, self.group)
-        s, i = merge_topk(all_s, all_i, k)
+        s, i = self.search_raw(queries, k)
         return s, i.to(torch.int64)
 
-    def replicated_rows(self) -> Tensor:
-        """The whole store on every rank (bf16 N x d): one all-gather of the shards over NVLink.
-        BASELINE.json config 5 replicates the 1 M x 256 store (512 MB) as the all-pairs queries.
-        Shards may differ by one row (`shard_range`); they are padded to the longest for the gather."""
+    def knn_graph(self, k: int, *, gather: bool = True, budget_bytes: int = 2 << 30) -> tuple[Tensor, Tensor]:
+        """All-pairs similarity graph over the sharded store (BASELINE.json config 5).
+
+        The QUERIES are sharded — rank r answers for its own rows — and the STORE rotates: step by
+        step every rank contributes the next chunk of its shard to one all-gather over NVLink and
+        searches the gathered rows with `KNN_CONTINUE`, so the running top-k lists of its queries
+        persist across all store blocks inside the search kernel's workspace.  No partial result is
+        ever gathered or merged, and a row's own entry is skipped inside the kernel.
+
+        gather=True  every rank returns the full graph (scores N×k fp32, indices N×k int64): one
+                     final all-gather of the finished lists;
+        gather=False a rank returns the lists of its own rows only (rows `shard_range(total, G, r)`)."""
         import torch.distributed as dist
 
-        sizes = [e - b for b, e in (shard_range(self.total_rows, self.world_size, r) for r in range(self.world_size))]
-        per = max(sizes)
-        local = self.local.embeddings
-        d = local.shape[1]
-        padded = torch.zeros((per, d), dtype=local.dtype, device=local.device)
-        padded[: local.shape[0]] = local
-        out = torch.empty((per * self.world_size, d), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, padded, group=self.group)
-        if all(sz == per for sz in sizes):
-            return out
-        return torch.cat([out[r * per: r * per + sizes[r]] for r in range(self.world_size)], dim=0)
-
-    def knn_graph(self, k: int, *, block: int = 131072) -> tuple[Tensor, Tensor]:
-        """All-pairs similarity graph over the sharded store (BASELINE.json config 5): every rank
-        searches ALL rows (replicated once over NVLink) against its shard in blocks with k + 1,
-        one all-gather of (score, index) + merge per block, self matches removed.  Every rank
-        returns the full graph: (scores N x k fp32, indices N x k int64)."""
         if self.total_rows is None:
             raise ValueError("knn_graph needs a store built with total_rows (the contiguous partition)")
-        rows_all = self.replicated_rows()
-        n = rows_all.shape[0]
-        rn_all = row_rnorm(rows_all)
-        dev = rows_all.device
-        out_s = torch.empty((n, k), dtype=torch.float32, device=dev)
-        out_i = torch.empty((n, k), dtype=torch.int64, device=dev)
-        for b in range(0, n, block):
-            e = min(n, b + block)
-            s, i = self.local.search_raw(rows_all[b:e], k + 1, query_rnorm=rn_all[b:e])
-            all_s, all_i = gather_partials(s, i, self.group)
-            s, i = merge_topk(all_s, all_i, k + 1)
-            s, i = drop_self_matches(s, i.to(torch.int64), torch.arange(b, e, device=dev), k)
-            out_s[b:e], out_i[b:e] = s, i
-        return out_s, out_i
+        self.local._check_k(k)
+        G, r = self.world_size, self.rank
+        ranges = [shard_range(self.total_rows, G, g) for g in range(G)]
+        sizes = [e - b for b, e in ranges]
+        local, d, dev = self.local.embeddings, self.local.dim, self.local.device
+        n_local = local.shape[0]
+        chunk, steps = graph_chunk_plan(sizes, d, budget_bytes)
+        scores = torch.empty((n_local, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((n_local, k), dtype=torch.int32, device=dev)
+        uniform = all(sz == sizes[0] for sz in sizes)
+        calls = []  # (rows, index_base) in search order
+        first = True
+        for step in range(steps):
+            c0 = step * chunk
+            cr = min(chunk, max(sizes) - c0)
+            if n_local >= c0 + cr:
+                send = local[c0:c0 + cr]
+            else:  # shards differ by one row: pad the short ones
+                send = torch.zeros((cr, d), dtype=local.dtype, device=dev)
+                if n_local > c0:
+                    send[: n_local - c0] = local[c0:]
+            gathered = torch.empty((G * cr, d), dtype=local.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, send.contiguous(), group=self.group)
+            rn = row_rnorm(gathered)
+            if uniform and steps == 1:
+                blocks = [(0, G * cr, 0)]  # the gathered buffer IS the store in global row order
+            else:
+                blocks = [(g * cr, min(cr, max(0, sizes[g] - c0)), ranges[g][0] + c0) for g in range(G)]
+                blocks = [b for b in blocks if b[1] > 0]
+            for bi, (off, rows, base) in enumerate(blocks):
+                last = step == steps - 1 and bi == len(blocks) - 1
+                flags = _lib.KNN_EXCLUDE_SELF | (0 if first else _lib.KNN_CONTINUE) | (0 if last else _lib.KNN_NO_FINALIZE)
+                if n_local:
+                    self.local.search_block(
+                        gathered[off:off + rows], rn[off:off + rows], base, local, self.local.rnorm, k, flags=flags,
+                        query_index_base=ranges[r][0], out_a=scores if last else None, out_b=idx if last else None,
+                    )
+                first = False
+                calls.append((rows, base))
+        self._last_graph_calls = calls
+        if not gather:
+            return scores, idx.to(torch.int64)
+        per = max(sizes)
+        if not uniform:
+            ps = torch.full((per, k), float("-inf"), dtype=torch.float32, device=dev)
+            pi = torch.full((per, k), -1, dtype=torch.int32, device=dev)
+            ps[:n_local], pi[:n_local] = scores, idx
+            scores, idx = ps, pi
+        all_s = torch.empty((G * per, k), dtype=torch.float32, device=dev)
+        all_i = torch.empty((G * per, k), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_s, scores, group=self.group)
+        dist.all_gather_into_tensor(all_i, idx, group=self.group)
+        if not uniform:
+            keep = torch.cat([torch.arange(g * per, g * per + sizes[g], device=dev) for g in range(G)])
+            all_s, all_i = all_s[keep], all_i[keep]
+        return all_s, all_i.to(torch.int64)
 
     def replicate_queries(self, host_queries: Tensor) -> Tensor:
         """Replicated device copy of a (pinned) host query matrix without sending it over PCIe once

@@ -67,9 +67,8 @@ def maps_to_rows(maps: Tensor, *, pool: str | None = None) -> Tensor:
     n, c, h, w = x.shape
     rows = torch.empty((n if pool else n * h * w, c), dtype=torch.bfloat16, device=x.device)
     if n:
-        rc = _lib.load().isx_maps_to_rows_bf16(
-            x.data_ptr(), n, c, h * w, int(pool is not None), rows.data_ptr(), _lib.stream_ptr(x.device)
-        )
+        with _lib.on_device(x) as stream:
+            rc = _lib.load().isx_maps_to_rows_bf16(x.data_ptr(), n, c, h * w, int(pool is not None), rows.data_ptr(), stream)
         _lib.check(rc, "isx_maps_to_rows_bf16")
     return rows
 

@@ -85,6 +85,23 @@ int isx_preprocess_apply(const void* in, int in_dtype, int layout, int B, int C,
 int isx_resize_bilinear(const void* in, int in_dtype, int layout, int B, int C, int H, int W,
                         int outH, int outW, float* out, isx_stream_t stream);
 
+/* Patch tiling (BASELINE.json north_star, stage 1: "with resize and patch tiling"; the reference has
+ * no counterpart — its only "patches" are feature-map cells, SURVEY.md §8c — so the semantics are the
+ * restatement oracle/oracle.py::preprocess_patches: cut every image into patch x patch windows at
+ * `stride` (full windows only: ny = (img_h - patch) / stride + 1, likewise nx), treat the windows as the
+ * tile batch of models/embedding.py:150-165 and preprocess them as above).  The windows are index
+ * arithmetic inside both passes' reads: no patch tensor is materialised.
+ * images: uint8, n_img x img_h x img_w x 3 (NHWC) or n_img x 3 x img_h x img_w (NCHW); C must be 3.
+ * out: (n_img * ny * nx) x 3 x outH x outW, patches in (image, py, px) order; batch statistics are
+ * over ALL patches (overlapping pixels count once per patch that holds them). */
+int isx_preprocess_patches_stats(const void* images, int layout, int n_img, int C, int img_h, int img_w, int patch,
+                                 int stride, int outH, int outW, float* mean, float* std, void* workspace,
+                                 size_t workspace_bytes, isx_stream_t stream);
+int isx_preprocess_patches_apply(const void* images, int layout, int n_img, int C, int img_h, int img_w, int patch,
+                                 int stride, int outH, int outW, const float* mean, const float* std, float eps,
+                                 int has_lo, float lo, int has_hi, float hi, void* out, int out_dtype,
+                                 isx_stream_t stream);
+
 /* ---- stage 2: L2-normalise (+ pool) + PCA projection ------------------------------------------
  * Replaces models/embedding.py:74 `F.normalize(x, p=2, dim=1)`, data.py:112-118
  * `get_flat_vectors`, models/decomposition.py:79-91 `PCA.forward` and the reshape/permute of
@@ -119,6 +136,12 @@ int isx_l2norm_project(const float* fmap, int B, int E, int h, int w, int pool, 
 int isx_l2norm_project_fp16(const float* fmap, int B, int E, int h, int w, int pool, int normalize,
                             const void* packed, int k, float* out, void* workspace,
                             size_t workspace_bytes, isx_stream_t stream);
+
+/* Stand-alone per-cell L2 normalisation, models/embedding.py:74 `F.normalize(x, p=2, dim=1)` as
+ * `EmbeddingModule.predict_step` (:57-76) returns it: out[b][e][c] = fmap[b][e][c] /
+ * max(||fmap[b][:][c]||_2, eps), IEEE division.  fmap, out: fp32 B x E x h x w (NCHW, contiguous,
+ * distinct buffers).  One pass: 4 bytes read + 4 written per element. */
+int isx_l2norm_cells(const float* fmap, int B, int E, int h, int w, float eps, float* out, isx_stream_t stream);
 
 /* ---- PCA.fit moments (models/decomposition.py:94-148) -------------------------------------------
  * mean[F] = column means of x (n x F fp32, row-major; :116) and cov[F x F] = Xc^T Xc / (n - 1) with
@@ -155,10 +178,33 @@ int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const
                    float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes,
                    isx_stream_t stream);
 
+/* Extended form.  flags:
+ *   ISX_KNN_CONTINUE      the workspace holds the running top-k lists of a previous call with the same
+ *                         q and k (same queries): this call adds another block of store rows to them —
+ *                         a store that arrives in pieces (ring / chunked all-gather) is searched
+ *                         without ever gathering partial results;
+ *   ISX_KNN_NO_FINALIZE   more blocks follow: outputs are not written (may be NULL);
+ *   ISX_KNN_EXCLUDE_SELF  query row r IS store row query_index_base + r (all-pairs graph) and is never
+ *                         its own neighbour;
+ *   ISX_KNN_PACKED        out_scores receives q x k 8-byte records {fp32 score, int32 index} instead of
+ *                         two arrays (out_idx unused): what ONE all-gather moves between shards.
+ * isx_knn_workspace_bytes depends on (q, k) only, so one workspace serves every block. */
+#define ISX_KNN_CONTINUE 1
+#define ISX_KNN_NO_FINALIZE 2
+#define ISX_KNN_EXCLUDE_SELF 4
+#define ISX_KNN_PACKED 8
+int isx_knn_search_ex(const void* store, const float* store_rnorm, int64_t n, const void* queries,
+                      const float* query_rnorm, int q, int d, int k, int64_t index_base,
+                      int64_t query_index_base, int flags, float* out_scores, int32_t* out_idx,
+                      void* workspace, size_t workspace_bytes, isx_stream_t stream);
+
 /* Merge g partial results (scores, idx: g x q x k, e.g. the NCCL all-gather of every shard's
  * local top-k) into q x k with the same ordering.  idx < 0 marks padding. */
 int isx_topk_merge(const float* scores, const int32_t* idx, int g, int q, int k, float* out_scores,
                    int32_t* out_idx, isx_stream_t stream);
+/* Same for packed records (g x q x k x {fp32 score, int32 index}, ISX_KNN_PACKED). */
+int isx_topk_merge_packed(const void* records, int g, int q, int k, float* out_scores, int32_t* out_idx,
+                          isx_stream_t stream);
 
 /* ---- ROI masks on the feature-map grid ---------------------------------------
  * geometry.py:14-65 `create_roi_mask`: rasterio.features.rasterize(shapes, out_shape=(hf, wf),

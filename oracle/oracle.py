@@ -13,7 +13,8 @@ Parity status
   `flat_vectors`, `pca_transform`, `pipeline_project(pool=None)`): **PINNED** against golden vectors
   produced by running the unmodified reference in the build container
   (`oracle/make_golden.py` -> `tests/golden/*.npz`, checked by `tests/test_oracle_golden.py`).
-* Stage 3 (`cosine_knn`, `topk_merge`) and `pool="mean"`: **parity unpinned** — the reference has
+* Stage 3 (`cosine_knn`, `topk_merge`), `pool="mean"` and patch tiling (`extract_patches`):
+  **parity unpinned** — the reference has
   no k-NN, pooling or merge code and no test for them.  The restatement is
   the composition of the reference's own idioms: `F.normalize` (models/embedding.py:74) and
   `torch.matmul` (models/decomposition.py:91), followed by a stable (score desc, index asc) top-k.
@@ -228,6 +229,41 @@ def preprocess(
     if max(h, w) > max_side_length:
         x = resize(x, max_side_length, side_ref="long")
     return normalize_per_channel(x, channel_means=channel_means, channel_stds=channel_stds, min_value=-3, max_value=3)
+
+
+def extract_patches(images_u8: np.ndarray, patch: int, stride: int | None = None, layout: int = NHWC) -> np.ndarray:
+    """Patch tiling (parity unpinned: the reference has no patch tiling).
+    Restatement: every image is cut into `patch` x `patch` windows whose top-left corners lie on a
+    `stride` grid; only full windows are kept (ny = (H - patch) // stride + 1, likewise nx); windows
+    are ordered (image, py, px) and returned in the input's layout, i.e. exactly the tile batch
+    `_collate_image_batch` (data.py:456-459) would stack had the windows been separate files."""
+    stride = patch if stride is None else stride
+    x = np.asarray(images_u8)
+    if layout == NHWC:
+        n, H, W, C = x.shape
+    else:
+        n, C, H, W = x.shape
+    ny, nx = (H - patch) // stride + 1, (W - patch) // stride + 1
+    out = []
+    for i in range(n):
+        for py in range(ny):
+            for px in range(nx):
+                y0, x0 = py * stride, px * stride
+                if layout == NHWC:
+                    out.append(x[i, y0:y0 + patch, x0:x0 + patch, :])
+                else:
+                    out.append(x[i, :, y0:y0 + patch, x0:x0 + patch])
+    return np.ascontiguousarray(np.stack(out, axis=0))
+
+
+def preprocess_patches(
+    images_u8: np.ndarray, patch: int, stride: int | None = None, *, max_side_length: int = 640, layout: int = NHWC,
+    channel_means: np.ndarray | None = None, channel_stds: np.ndarray | None = None,
+) -> np.ndarray:
+    """Patch tiling followed by models/embedding.py:150-165 `preprocess` on the window batch
+    (statistics over all windows: a pixel covered by several windows counts once per window)."""
+    return preprocess(extract_patches(images_u8, patch, stride, layout), max_side_length=max_side_length, layout=layout,
+                      channel_means=channel_means, channel_stds=channel_stds)
 
 
 # ----------------------------------------------------------------------------------------------

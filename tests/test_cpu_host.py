@@ -49,9 +49,15 @@ def test_no_cpu_fallback():
         T.resize(torch.zeros(3, 8, 8, dtype=torch.uint8), 4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         search.EmbeddingStore(torch.zeros(4, 8))
-    pca = PCA().fit(torch.randn(50, 6))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
-        pca.transform(torch.randn(3, 6))
+        PCA().fit(torch.randn(50, 6))  # the moments come from the sm_100a kernels: CUDA tensors only
+    from imagescry_b200.models.embedding import l2_normalize_cells
+    from imagescry_b200.image.transforms import preprocess_patches
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        l2_normalize_cells(torch.zeros(1, 8, 2, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        preprocess_patches(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), 4)
 
 
 def test_product_never_imports_oracle():
@@ -99,30 +105,21 @@ def test_batch_dataclasses_and_typechecking():
         ib.indices = torch.arange(3)  # frozen
 
 
-def test_pca_fit_component_selection():
-    """Component counts of the reference's fixtures (test_decomposition.py:42-81,84-124)."""
-    from torch.distributions import MultivariateNormal
+def test_pca_component_selection_rule():
+    """The selection rule of decomposition.py:128-137 on the explained-variance ratios of the
+    reference's own fixtures (test_decomposition.py:42-81,84-124): expected component counts."""
+    from imagescry_b200.models.decomposition import PCA, select_num_components
 
-    from imagescry_b200.models.decomposition import PCA
-
-    locs = torch.tensor([0.0, 1.0, -1.0, 0.0])
-    torch.manual_seed(1234)
-    unc = MultivariateNormal(loc=locs, covariance_matrix=torch.eye(4)).sample((1000,))
-    for mev, want in [(0.2, 1), (0.4, 2), (0.6, 3), (1.0, 4)]:
-        assert PCA(min_explained_variance=mev).fit(unc).num_components == want
-    torch.manual_seed(1234)
-    cov = torch.tensor([[1.0, 0.5, 0, 0], [0.5, 1.0, 0, 0], [0, 0, 1.0, -0.5], [0, 0, -0.5, 1.0]])
-    cor = MultivariateNormal(loc=locs, covariance_matrix=cov).sample((1000,))
-    for mev, want in [(0.2, 1), (0.4, 2), (0.6, 2), (0.8, 3), (1.0, 4)]:
-        pca = PCA(min_explained_variance=mev).fit(cor)
-        assert pca.num_components == want
-        assert pca.explained_variance[:want].sum() >= mev - 1e-6
     g = np.load(os.path.join(REPO, "tests", "golden", "embed_pca.npz"))
-    pca = PCA(min_explained_variance=0.8).fit(torch.from_numpy(g["pca_cor_x"]))
-    assert np.allclose(pca.feature_means.numpy(), g["pca_cor_means"], atol=1e-6)
-    # SVD sign is arbitrary: compare components up to sign
-    dots = np.abs((pca.component_vectors.numpy() * g["pca_cor_comps"]).sum(axis=0))
-    assert np.allclose(dots, 1.0, atol=1e-4)
+    unc = torch.from_numpy(g["pca_unc_explained"])
+    for mev, want in [(0.2, 1), (0.4, 2), (0.6, 3), (1.0, 4)]:
+        assert select_num_components(unc, 1, None, mev) == want
+    cor = torch.from_numpy(g["pca_cor_explained"])
+    for mev, want in [(0.2, 1), (0.4, 2), (0.6, 2), (0.8, 3), (1.0, 4)]:
+        k = select_num_components(cor, 1, None, mev)
+        assert k == want and cor[:k].sum() >= mev - 1e-6
+    assert select_num_components(cor, 3, None, 0.1) == 3   # min_num_components
+    assert select_num_components(cor, 1, 2, 1.0) == 2      # max_num_components
     with pytest.raises(ValueError):
         PCA(min_num_components=0)
     with pytest.raises(ValueError):
@@ -131,8 +128,37 @@ def test_pca_fit_component_selection():
         PCA(min_explained_variance=1.5)
     with pytest.raises(RuntimeError, match="not fitted"):
         PCA().transform(torch.zeros(2, 3))
-    sd = pca.state_dict()
-    assert {"feature_means", "component_vectors", "_fitted"} <= set(sd)
+    assert {"feature_means", "component_vectors", "_fitted"} <= set(PCA().state_dict())
+    # re-assigned weights drop the packed operand
+    p = PCA(num_features=4, num_components=2)
+    p.__dict__["_packed"] = torch.zeros(1)
+    p.component_vectors = torch.nn.Parameter(torch.zeros(4, 2), requires_grad=False)
+    assert p._packed is None
+    p.__dict__["_packed"] = torch.zeros(1)
+    p.load_state_dict(PCA(num_features=4, num_components=2).state_dict())
+    assert p._packed is None
+
+
+def test_patch_grid_and_graph_chunk_plan():
+    from imagescry_b200.image.transforms import patch_grid
+    from imagescry_b200.search import graph_chunk_plan, pack_records, unpack_records
+
+    assert patch_grid(2048, 2048, 512) == (4, 4)
+    assert patch_grid(100, 130, 32, 16) == (5, 7)
+    assert patch_grid(32, 32, 32, 7) == (1, 1)
+    with pytest.raises(ValueError):
+        patch_grid(31, 64, 32)
+    for img_h, img_w, p_, s_ in [(100, 130, 32, 16), (64, 64, 64, 64), (50, 77, 20, 9)]:
+        x = np.zeros((1, img_h, img_w, 3), dtype=np.uint8)
+        ny, nx = patch_grid(img_h, img_w, p_, s_)
+        assert O.extract_patches(x, p_, s_).shape == (ny * nx, p_, p_, 3)
+    assert graph_chunk_plan([125000] * 8, 256, 2 << 30) == (125000, 1)
+    chunk, steps = graph_chunk_plan([2502, 2501], 64, 64 * 700 * 2 * 2)
+    assert chunk == 700 and steps == 4
+    s = torch.tensor([[1.5, float("-inf")]])
+    i = torch.tensor([[7, -1]], dtype=torch.int32)
+    us, ui = unpack_records(pack_records(s, i))
+    assert torch.equal(us, s) and torch.equal(ui, i)
 
 
 def test_shard_range_partition():
@@ -153,7 +179,7 @@ _WORKER = r"""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["ISX_REPO"])
-from imagescry_b200.search import gather_partials, shard_range
+from imagescry_b200.search import gather_partials, gather_records, pack_records, unpack_records, shard_range
 from oracle import oracle as O
 dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{os.environ['ISX_PORT']}",
                         rank=int(os.environ["ISX_RANK"]), world_size=2)
@@ -170,6 +196,11 @@ assert all_s.shape == (2, 9, 5) and all_i.shape == (2, 9, 5)
 ms, mi = O.topk_merge(all_s.numpy(), all_i.numpy(), 5)
 gs, gi = O.cosine_knn(store, queries, 5)
 assert np.array_equal(mi, gi) and np.array_equal(ms, gs), rank
+# the packed form: ONE all-gather of 8-byte (score, index) records
+rec = gather_records(pack_records(torch.from_numpy(ls), torch.from_numpy(li.astype(np.int32))))
+assert rec.shape == (2, 9, 5) and rec.dtype == torch.int64
+us, ui = unpack_records(rec)
+assert torch.equal(us, all_s) and torch.equal(ui, all_i)
 dist.barrier()
 dist.destroy_process_group()
 print("OK", rank)
