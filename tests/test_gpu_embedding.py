@@ -32,13 +32,15 @@ def dev(a):
 
 # ------------------------------------------------------------------------------------ a6
 def test_l2_normalize_cells_golden(golden):
-    """The reference's own `nn.functional.normalize(x, p=2, dim=1)` outputs: within 2 ulp (the
-    reference's fp32 norm reduction order is torch's; the quotient itself is the IEEE division)."""
+    """The reference's own `nn.functional.normalize(x, p=2, dim=1)` outputs.  The quotient is the IEEE
+    division; the kernel's norm is within an ulp of exact (fp64 fold), torch-CPU's fp32 norm reduction
+    carries a few ulp of its own, so the two differ by a few ulp (bar: 1e-3 relative)."""
     g = golden("embed_pca")
     for src, want in (("eb_fmap", "eb_l2"), ("pipe_fmap", "pipe_l2")):
         out = l2_normalize_cells(dev(g[src])).cpu().numpy()
         assert out.shape == g[want].shape
-        assert ulp_diff(out, g[want]).max() <= 2, (src, ulp_diff(out, g[want]).max())
+        assert ulp_diff(out, g[want]).max() <= 6, (src, ulp_diff(out, g[want]).max())
+        assert np.abs(out - g[want]).max() <= 1e-6 * np.abs(g[want]).max()
 
 
 @pytest.mark.parametrize(
@@ -143,7 +145,8 @@ def test_embed_images_and_pipeline_predict_over_batches():
 PATCH_CASES = [
     # (n, H, W, patch, stride, out_hw)
     (2, 64, 96, 32, 32, None),      # exact tiling, no resize
-    (1, 100, 130, 32, 16, None),    # overlapping windows, remainder cropped
+    (1, 100, 130, 32, 16, None),    # overlapping windows, remainder cropped (sampling kernel with scale 1)
+    (1, 96, 128, 32, 16, None),     # overlapping windows on 4-pixel-aligned geometry: table-lookup apply
     (2, 70, 90, 24, 24, (12, 12)),  # 2x down-scale of every window
     (1, 128, 160, 64, 48, (37, 37)),
     (3, 40, 40, 40, 40, (16, 16)),  # one window per image
