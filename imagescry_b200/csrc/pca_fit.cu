@@ -14,8 +14,12 @@
 //   K6d cov_syrk_kernel       tcgen05 SYRK: 128 x 256 tiles of Xc^T Xc that touch the upper triangle,
 //                             split-K over the chunk's rows; operands by TMA (128B swizzle), three MMAs
 //                             per k-step (hi.hi + hi.lo + lo.hi: fp32-class products) into one fp32 TMEM
-//                             accumulator; every (tile, split) owns a slot of the partial buffer and adds
-//                             to it chunk after chunk (stream-ordered, no atomics: deterministic)
+//                             accumulator pair (hi.hi in one, the small cross terms in the other); every
+//                             (tile, split) owns a slot of the partial buffer and adds to it chunk after
+//                             chunk (stream-ordered, no atomics: deterministic).  The tensor core's fp32
+//                             accumulation TRUNCATES (measured: -2.3e-5 relative after 750 accumulating
+//                             MMAs of same-sign products), so one accumulation covers at most 1024 rows
+//                             (64 hi.hi MMAs, bias < 2e-6) before it is drained with round-to-nearest adds
 //   K6e cov_finalize_kernel   fold the split partials in fp64 in a fixed order, divide by n - 1, mirror
 #include "common.cuh"
 
@@ -36,7 +40,7 @@ constexpr uint32_t kSyrkBPart = SN_ * SK_ * 2;  // 32 KB
 constexpr uint32_t kSyrkStageBytes = 2 * kSyrkAPart + 2 * kSyrkBPart;  // 96 KB
 constexpr uint32_t kSyrkBarOff = kSyrkStages * kSyrkStageBytes;
 constexpr uint32_t kSyrkSmem = kSyrkBarOff + 64 + 1024;
-constexpr size_t kSplitBufferBytes = 64ull << 20;  // budget of the transposed hi + lo chunk buffers
+constexpr int kSyrkRowsPerAcc = 1024;  // rows one TMEM accumulation covers (truncation bias, see the header)
 
 struct FitPlan {
   int chunks;                // column-sum row chunks
@@ -53,8 +57,7 @@ FitPlan fit_plan(long long n, int F) {
   p.rows_per_chunk = (n + p.chunks - 1) / p.chunks;
   p.f_pad = (F + SN_ - 1) / SN_ * SN_;
   const long long n_pad = (n + SK_ - 1) / SK_ * SK_;
-  const long long fit = static_cast<long long>(kSplitBufferBytes / (4ull * p.f_pad)) / SK_ * SK_;
-  p.nc = std::min<long long>(n_pad, std::max<long long>(SK_ * kSyrkSplits, fit));
+  p.nc = std::min<long long>(n_pad, static_cast<long long>(kSyrkSplits) * kSyrkRowsPerAcc);
   p.mt = p.f_pad / SM_;
   p.nt = p.f_pad / SN_;
   p.tiles = 0;
@@ -149,7 +152,7 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
     mbar_init(acc_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_ptr, SN_); tmem_relinquish(); }
+  if (warp == 2) { tmem_alloc(tmem_ptr, 2 * SN_); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -188,9 +191,10 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
           const uint32_t o = k * 32;
           const uint64_t dah = make_kmajor_sw128_desc(a_hi + o), dal = make_kmajor_sw128_desc(a_lo + o);
           const uint64_t dbh = make_kmajor_sw128_desc(b_hi + o), dbl = make_kmajor_sw128_desc(b_lo + o);
-          tc_mma_f16(tmem_base, dah, dbh, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-          tc_mma_f16(tmem_base, dah, dbl, idesc, 1);
-          tc_mma_f16(tmem_base, dal, dbh, idesc, 1);
+          const uint32_t first = (kb != kb0 || k != 0) ? 1u : 0u;
+          tc_mma_f16(tmem_base, dah, dbh, idesc, first);        // columns [0, 256): hi . hi
+          tc_mma_f16(tmem_base + SN_, dah, dbl, idesc, first);  // columns [256, 512): the cross terms
+          tc_mma_f16(tmem_base + SN_, dal, dbh, idesc, 1);
         }
         tc_commit(&empty_bar[stage]);
         if (++stage == kSyrkStages) { stage = 0; phase ^= 1; }
@@ -208,10 +212,14 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < SN_; c0 += 32) {
-      uint32_t r[32];
+      uint32_t r[32], r2[32];
       if (kb1 > kb0) {
         tmem_ld_32x32(taddr + c0, r);
+        tmem_ld_32x32(taddr + SN_ + c0, r2);
         tc_wait_ld_regs(r);
+        tc_wait_ld_regs(r2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
@@ -233,7 +241,7 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, SN_);
+    tmem_dealloc(tmem_base, 2 * SN_);
   }
 }
 

@@ -38,7 +38,7 @@ def main():
     import torch
 
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["knn", "preprocess", "project"])
+    ap.add_argument("what", choices=["knn", "preprocess", "project", "l2norm", "graph", "pcafit"])
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--q", type=int, default=10_000)
     ap.add_argument("--d", type=int, default=1280)
@@ -67,6 +67,29 @@ def main():
         tf = 2.0 * a.q * a.n * a.d / (ms * 1e-3) / 1e12
         print(json.dumps({"case": f"knn n={a.n} q={a.q} d={a.d} k={a.k}", "ms": ts, "tflops": tf,
                           "frac_sustained": tf / peaks["bf16_tflops_sustained"], "frac_burst": tf / peaks["bf16_tflops"]}))
+    elif a.what == "l2norm":
+        from imagescry_b200.models.embedding import l2_normalize_cells
+
+        B, E, h, w = a.batch, 1280, 16, 16
+        fmap = torch.randn((B, E, h, w), generator=g, device=dev)
+        ts = timeit(lambda: l2_normalize_cells(fmap), a.iters, a.warm)
+        gbs = fmap.numel() * 8 / (min(ts) * 1e-3) / 1e9
+        print(json.dumps({"case": f"l2norm B={B}", "ms": ts, "GBps": gbs, "frac_hbm": gbs / peaks["hbm_gbs"]}))
+    elif a.what == "graph":
+        from imagescry_b200.search import EmbeddingStore
+
+        store = torch.randn((a.n, a.d), generator=g, device=dev).to(torch.bfloat16)
+        st = EmbeddingStore(store)
+        ts = timeit(lambda: st.knn_graph(a.k), a.iters, a.warm)
+        tf = 2.0 * a.n * a.n * a.d / (min(ts) * 1e-3) / 1e12
+        print(json.dumps({"case": f"graph n={a.n} d={a.d} k={a.k}", "ms": ts, "tflops": tf, "frac_sustained": tf / peaks["bf16_tflops_sustained"]}))
+    elif a.what == "pcafit":
+        from imagescry_b200.models.decomposition import PCA
+
+        x = torch.randn((a.n, a.d), generator=g, device=dev) + 0.5
+        pca = PCA(min_num_components=64, max_num_components=64).cuda()
+        ts = timeit(lambda: pca._moments(x), a.iters, a.warm)
+        print(json.dumps({"case": f"pca moments n={a.n} F={a.d}", "ms": ts}))
     elif a.what == "preprocess":
         from imagescry_b200.image.transforms import preprocess_tiles
 
