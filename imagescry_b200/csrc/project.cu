@@ -838,6 +838,310 @@ l2norm_project_tmem_kernel(const __grid_constant__ CUtensorMap tmap_whi, const _
 }
 
 // ------------------------------------------------------------------------------------------
+// K3d: the per-cell kernel with NO raw staging (CTA pairs; the default for NCHW feature maps).
+// Shared memory carries only the weight tiles and the outgoing rows:
+//   * the transform warps read the fp32 map straight from global memory — cells are the contiguous
+//     dimension, so a warp's load of one channel is one 128-byte line — one k-block ahead in registers
+//     (32 KB of loads in flight per SM), accumulate the cells' sums of squares, split to bf16 hi/lo and
+//     write the A operand with tcgen05.st into TENSOR MEMORY (4 stages x 64 columns next to the
+//     256-column accumulator); the MMAs take A from there (TS form);
+//   * warp 3 asks the TMA unit to pull the boxes of the map into L2 a few k-blocks ahead;
+//   * the epilogue scales by 1/||x||, adds the bias and hands 128-row x 32-column boxes (128-byte rows,
+//     128B swizzle) to TMA stores: every global write is a full line instead of 16-byte pieces of
+//     1 KB-strided rows.
+// Per k-block a CTA's shared-memory port now moves 32 KB of weights in and 96 KB of weight reads out
+// (its half and the peer's) = 1000 cycles at 128 B/clk, against 1536 tensor cycles: the kernel is bound
+// by the three tensor passes that fp32-class accuracy costs, no longer by shared memory.
+//   warp 0 weight TMA, warp 1 MMA issuer (leader), warp 2 TMEM alloc, warp 3 L2 prefetch,
+//   warps 4-7 epilogue, warps 8-23 transform: warp tw owns TMEM lane quarter tw % 4
+//   (cells 32 (tw % 4) + lane of the tile) and features 16 (tw / 4) .. + 15 of every k-block.
+// ------------------------------------------------------------------------------------------
+struct ProjDSmem {
+  static constexpr int A_STAGES = 4, W_STAGES = 4, OUT_BUFS = 4;
+  static constexpr uint32_t W_PART_BYTES = (kMaxComponents / 2) * PK * 2;  // 16 KB
+  static constexpr uint32_t W_STAGE_BYTES = 2 * W_PART_BYTES;              // hi + lo
+  static constexpr uint32_t OUT_BUF_BYTES = PM * 32 * 4;                   // 128 rows x 32 columns fp32 = 16 KB
+  static constexpr uint32_t kWOff = 0;
+  static constexpr uint32_t kOutOff = kWOff + W_STAGES * W_STAGE_BYTES;
+  static constexpr uint32_t kSsOff = kOutOff + OUT_BUFS * OUT_BUF_BYTES;   // [2][4 feature groups][128 rows]
+  static constexpr uint32_t kBarOff = kSsOff + 2 * 4 * PM * 4;
+  static constexpr uint32_t kNumBars = 2 * A_STAGES + 2 * W_STAGES + 2 + 4;
+  static constexpr uint32_t kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr uint32_t kTotal = kTmemPtrOff + 16;
+  static constexpr uint32_t kDynamicBytes = kTotal + 1024;
+  static constexpr uint32_t kAColumn0 = kMaxComponents;  // first A column in TMEM
+};
+
+__global__ void __launch_bounds__(kProjTThreads, 1)
+l2norm_project_direct_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_constant__ CUtensorMap tmap_wlo,
+                             const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_out,
+                             const ProjParams p) {
+  using L = ProjDSmem;
+  constexpr int A_STAGES = L::A_STAGES, W_STAGES = L::W_STAGES;
+  const uint32_t rank = cluster_ctarank();
+  const long long unit = blockIdx.x / 2, num_units = gridDim.x / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* a_full = bars;                       // [A]   16 transform warps x 2 CTAs (on the leader)
+  uint64_t* a_empty = a_full + A_STAGES;         // [A]   tcgen05.commit (both CTAs)
+  uint64_t* w_full = a_empty + A_STAGES;         // [W]   TMA of both CTAs (on the leader)
+  uint64_t* w_empty = w_full + W_STAGES;         // [W]   tcgen05.commit (both CTAs)
+  uint64_t* tmem_full = w_empty + W_STAGES;      // accumulator complete (both CTAs)
+  uint64_t* tmem_empty = tmem_full + 1;          // 4 epilogue warps x 2 CTAs (on the leader)
+  uint64_t* ss_full = tmem_empty + 1;            // [2]   16 transform warps
+  uint64_t* ss_empty = ss_full + 2;              // [2]   4 epilogue warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
+  float* ss_s = reinterpret_cast<float*>(smem + L::kSsOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.E + PK - 1) / PK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_whi);
+    prefetch_tmap(&tmap_wlo);
+    prefetch_tmap(&tmap_out);
+    if (p.prefetch) prefetch_tmap(&tmap_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 16 * 2); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&w_full[i], 2); mbar_init(&w_empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4 * 2);
+    for (int i = 0; i < 2; ++i) { mbar_init(&ss_full[i], 16); mbar_init(&ss_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int w_rows = p.k_pad / 2;
+  const uint32_t w_part_bytes = static_cast<uint32_t>(w_rows) * PK * 2;
+  const long long my_tiles = (p.tiles - unit + num_units - 1) / num_units;
+  const long long total_seq = my_tiles * num_kb;
+
+  if (warp == 0) {
+    // ===================== weight TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const int32_t row0 = static_cast<int32_t>(rank) * w_rows;
+      int kb = 0;
+      for (long long seq = 0; seq < total_seq; ++seq) {
+        mbar_wait(&w_empty[stage], phase ^ 1);
+        uint8_t* dst = smem + L::kWOff + stage * L::W_STAGE_BYTES;
+        mbar_arrive_expect_tx_leader(&w_full[stage], 2 * w_part_bytes);
+        tma_load_2d_pair(dst, &tmap_whi, &w_full[stage], kb * PK, row0, kEvictLast);
+        tma_load_2d_pair(dst + L::W_PART_BYTES, &tmap_wlo, &w_full[stage], kb * PK, row0, kEvictLast);
+        if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+        if (++kb == num_kb) kb = 0;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(/*bf16*/ 1, PM * 2, static_cast<uint32_t>(p.k_pad));
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, tph = 0;
+      for (long long tile = 0; tile < my_tiles; ++tile) {
+        mbar_wait(tmem_empty, tph ^ 1);  // the epilogues of both CTAs drained the accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&w_full[ws], wph);
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t a_hi = tmem_base + L::kAColumn0 + as * 64;
+          const uint32_t a_lo = a_hi + 32;
+          const uint32_t w_hi = smem_u32(smem + L::kWOff + ws * L::W_STAGE_BYTES);
+          const uint32_t w_lo = w_hi + L::W_PART_BYTES;
+#pragma unroll
+          for (int k = 0; k < PK / P_UMMA_K; ++k) {
+            const uint64_t dwh = make_kmajor_sw128_desc(w_hi + k * P_UMMA_K * 2);
+            const uint64_t dwl = make_kmajor_sw128_desc(w_lo + k * P_UMMA_K * 2);
+            tc_mma_f16_pair_ts(tmem_base, a_hi + k * 8, dwh, idesc, (kb | k) != 0);
+            tc_mma_f16_pair_ts(tmem_base, a_lo + k * 8, dwh, idesc, 1);
+            tc_mma_f16_pair_ts(tmem_base, a_hi + k * 8, dwl, idesc, 1);
+          }
+          tc_commit_pair(&a_empty[as]);
+          tc_commit_pair(&w_empty[ws]);
+          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+        }
+        tc_commit_pair(tmem_full);
+        tph ^= 1;
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== L2 prefetcher =====================
+    // boxes of the map (128 cells x 64 features) are requested kPrefetchDepth k-blocks ahead of the
+    // transform warps, paced by the a_empty barriers, so their loads find the lines in L2
+    if (lane == 0 && p.prefetch) {
+      constexpr int kPrefetchDepth = 8;
+      auto prefetch = [&](long long seq) {
+        const long long tile_iter = seq / num_kb;
+        const int kb = static_cast<int>(seq - tile_iter * num_kb);
+        const long long R0 = ((unit + tile_iter * num_units) * 2 + rank) * PM;
+        if (R0 >= p.m_total) return;
+        const long long img = R0 / p.hw;
+        const int cell = static_cast<int>(R0 - img * p.hw);
+        asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                         reinterpret_cast<uint64_t>(&tmap_x)),
+                     "r"(cell), "r"(kb * PK), "r"(static_cast<int32_t>(img))
+                     : "memory");
+      };
+      for (long long s2 = 0; s2 < kPrefetchDepth && s2 < total_seq; ++s2) prefetch(s2);
+      for (long long seq = 0; seq + kPrefetchDepth < total_seq; ++seq) {
+        mbar_wait(&a_empty[seq % A_STAGES], static_cast<uint32_t>(((seq / A_STAGES) & 1) ^ 1));
+        prefetch(seq + kPrefetchDepth);
+      }
+    }
+  } else if (warp >= kTransformWarp0) {
+    // ===================== transform: fp32 map (global) -> bf16 hi/lo (TMEM) =====================
+    const int tw = warp - kTransformWarp0;
+    const int lq = tw & 3;            // == warp % 4: the TMEM lane quarter this warp may access
+    const int fg = tw >> 2;           // feature group: 16 features of the k-block
+    const int m = lq * 32 + lane;     // row (cell) inside the tile
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + L::kAColumn0 + fg * 8;
+    const long long hw = p.hw;
+    // load cursor: one k-block ahead of the convert cursor
+    long long ld_tile = 0;
+    int ld_kb = 0;
+    const float* ld_base = nullptr;
+    bool ld_valid = false;
+    auto seek = [&](long long tile_iter) {
+      const long long R = ((unit + tile_iter * num_units) * 2 + rank) * PM + m;
+      ld_valid = tile_iter < my_tiles && R < p.m_total;
+      const long long img = ld_valid ? R / hw : 0;  // once per tile
+      const long long cell = ld_valid ? R - img * hw : 0;
+      ld_base = p.fmap + img * p.E * hw + cell;
+    };
+    seek(0);
+    auto ld_f32 = [](const float* ptr) {
+      float v;
+      asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+      return v;
+    };
+    // E % 16 == 0 (host-checked): a thread's 16 features of a k-block exist together or not at all
+    auto load_block = [&](float (&x)[16]) {
+      const int f0 = ld_kb * PK + fg * 16;
+      const float* src = ld_base + static_cast<long long>(f0) * hw;
+      const bool live = ld_valid && f0 < p.E;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = live ? ld_f32(src + i * hw) : 0.f;
+      if (++ld_kb == num_kb) { ld_kb = 0; seek(++ld_tile); }
+    };
+    float ss = 0.f;
+    uint32_t as = 0, aph = 0, sst = 0, ssph = 0;
+    int pr_kb = 0;
+    float x[16];
+    if (total_seq > 0) load_block(x);
+    for (long long seq = 0; seq < total_seq; ++seq) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a = x[2 * i], b = x[2 * i + 1];
+        ss = fmaf(a, a, ss);
+        ss = fmaf(b, b, ss);
+        // hi = x truncated to bf16 (a mask); lo = RN_bf16(x - hi): |x - hi - lo| <= 2^-16 |x|
+        const uint32_t ab = __float_as_uint(a), bb = __float_as_uint(b);
+        hi[i] = __byte_perm(ab, bb, 0x7632);
+        const float la = a - __uint_as_float(ab & 0xFFFF0000u);
+        const float lb = b - __uint_as_float(bb & 0xFFFF0000u);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(la, lb);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      // the next k-block's loads go out now (x is free) and fly while this one is handed to the MMA;
+      // the other 15 transform warps of the SM cover the rest of their latency
+      if (seq + 1 < total_seq) load_block(x);
+      mbar_wait(&a_empty[as], aph ^ 1);
+      tc_fence_after();
+      tmem_st_32x8(t_row + as * 64, hi);
+      tmem_st_32x8(t_row + as * 64 + 32, lo);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&a_full[as]);
+      if (++as == A_STAGES) { as = 0; aph ^= 1; }
+      if (++pr_kb == num_kb) {
+        // last k-block of the tile: publish this warp's share of the rows' sums of squares
+        pr_kb = 0;
+        mbar_wait(&ss_empty[sst], ssph ^ 1);
+        ss_s[(sst * 4 + fg) * PM + m] = ss;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ss_full[sst]);
+        ss = 0.f;
+        if (++sst == 2) { sst = 0; ssph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter
+    const int row = ew * 32 + lane;
+    const int et = threadIdx.x - 4 * 32;  // 0..127
+    uint32_t sst = 0, ssph = 0, tph = 0, ob = 0;
+    auto epi_bar = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    for (long long tile = unit; tile < p.tiles; tile += num_units) {
+      const long long R0 = (tile * 2 + rank) * PM;
+      mbar_wait(&ss_full[sst], ssph);
+      float rn = 1.0f;
+      if (p.normalize) {
+        const float* sp = ss_s + sst * 4 * PM + row;
+        const float ssum = (sp[0] + sp[PM]) + (sp[2 * PM] + sp[3 * PM]);
+        rn = 1.0f / fmaxf(sqrtf(ssum), 1e-12f);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ss_empty[sst]);
+      if (++sst == 2) { sst = 0; ssph ^= 1; }
+      mbar_wait(tmem_full, tph);
+      tph ^= 1;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.k_pad; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c0, r);
+        tc_wait_ld_regs(r);
+        if (c0 + 32 >= p.k_pad) {
+          // every TMEM read of this tile has landed: the MMAs of the next tile may start
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tmem_empty);
+        }
+        // the store that last read this staging buffer (OUT_BUFS boxes ago) must have drained it
+        if (et == 0) tma_store_wait_read<L::OUT_BUFS - 1>();
+        epi_bar();
+        uint8_t* obuf = smem + L::kOutOff + ob * L::OUT_BUF_BYTES + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bz = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
+          float4 v;
+          v.x = fmaf(__uint_as_float(r[4 * j + 0]), rn, bz.x);
+          v.y = fmaf(__uint_as_float(r[4 * j + 1]), rn, bz.y);
+          v.z = fmaf(__uint_as_float(r[4 * j + 2]), rn, bz.z);
+          v.w = fmaf(__uint_as_float(r[4 * j + 3]), rn, bz.w);
+          *reinterpret_cast<float4*>(obuf + ((j ^ (row & 7)) << 4)) = v;  // 128B swizzle
+        }
+        fence_proxy_async_smem();
+        epi_bar();
+        if (et == 0) {
+          tma_store_2d(&tmap_out, smem + L::kOutOff + ob * L::OUT_BUF_BYTES, c0, static_cast<int32_t>(R0));
+          tma_store_commit();
+        }
+        if (++ob == L::OUT_BUFS) ob = 0;
+      }
+    }
+    if (et == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K3p: pooled[b][e] = (1/hw) * sum_cells x[b][e][cell] * rnorm[b][cell]  — one pass over the map.
 // One CTA per image at a time; 16-cell slabs [E][16] double-buffered in shared memory via cp.async.
 // ------------------------------------------------------------------------------------------
@@ -1146,10 +1450,35 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
     // tests): staged = bf16 operand tiles in shared memory, tmem = A operand in tensor memory,
     // reg = register-path loads without raw staging.  Read per call (a getenv, not on any hot loop).
     const char* mode_env = getenv("ISX_PROJECT_MODE");
-    const int mode = (mode_env && mode_env[0] == 't') ? 0 : (mode_env && mode_env[0] == 'r') ? 2 : 1;
+    const int mode = (mode_env && mode_env[0] == 't') ? 0 : (mode_env && mode_env[0] == 'r') ? 2
+                     : (mode_env && mode_env[0] == 's') ? 1 : 3;  // default: direct (K3d)
     if (p.prefetch && fast) {
       p.fast = 1;
       return launch_project_kernel<-1, 2>(twf, twl, tx, p, grid, stream);
+    }
+    // K3d: any map shape (the loads are per-thread); the TMA-store epilogue needs 16-byte output rows
+    if (mode == 3 && k % 4 == 0 && E % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && m_total < (1ll << 31)) {
+      CUtensorMap tout;
+      rc = encode_tmap_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, static_cast<uint64_t>(m_total),
+                          static_cast<uint64_t>(k), static_cast<uint64_t>(k) * 4, PM, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != ISX_OK) return rc;
+      auto kern = l2norm_project_direct_kernel;
+      const int smem = static_cast<int>(ProjDSmem::kDynamicBytes);
+      ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>(grid));
+      cfg.blockDim = dim3(kProjTThreads);
+      cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      ISX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, twh, twl, tx, tout, p));
+      return ISX_OK;
     }
     if (p.prefetch && mode == 0) {
       auto kern = l2norm_project_tmem_kernel;
@@ -1170,7 +1499,7 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
       ISX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, twh, twl, tx, p));
       return ISX_OK;
     }
-    if (p.prefetch && mode == 1) return launch_project_kernel<-1, 2>(twh, twl, tx, p, grid, stream);
+    if (p.prefetch && (mode == 1 || mode == 3)) return launch_project_kernel<-1, 2>(twh, twl, tx, p, grid, stream);
   }
   if (E % PK == 0 && hw == 256) return launch_project_kernel<256, NCTA>(twh, twl, tx, p, grid, stream);
   if (E % PK == 0 && hw == 64) return launch_project_kernel<64, NCTA>(twh, twl, tx, p, grid, stream);

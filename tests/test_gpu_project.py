@@ -223,9 +223,10 @@ def test_pca_fit_gpu_moments_and_components(golden):
     assert out.shape == (64, 8) and torch.isfinite(out).all()
 
 
-@pytest.mark.parametrize("mode", ["staged", "tmem", "reg"])
+@pytest.mark.parametrize("mode", ["direct", "staged", "tmem", "reg"])
 def test_per_cell_kernel_variants_agree(mode, monkeypatch):
-    """The three per-cell kernels (operand tiles in shared memory / A operand in tensor memory /
+    """The per-cell kernels (direct global loads + A operand in tensor memory + TMA-store epilogue, the
+    default / operand tiles in shared memory / A operand in tensor memory with a raw ring /
     register-path loads) are selected by ISX_PROJECT_MODE; each must meet the oracle."""
     import torch
 
