@@ -838,7 +838,12 @@ l2norm_project_tmem_kernel(const __grid_constant__ CUtensorMap tmap_whi, const _
 }
 
 // ------------------------------------------------------------------------------------------
-// K3d: the per-cell kernel with NO raw staging (CTA pairs; the default for NCHW feature maps).
+// K3d: the per-cell kernel with NO raw staging (CTA pairs; the default for map shapes the TMA boxes of
+// the staged kernel cannot express, e.g. 7 x 10 cells; ISX_PROJECT_MODE=direct forces it).
+// Measured at config 3b it runs at the staged kernel's speed (1.86 against 1.77 ms): with the raw ring
+// and the A tiles gone from shared memory the port carries 128 KB per k-block instead of 272 KB and
+// nothing got faster, which is what shows that the three tensor passes (1.15 PFLOP/s issued next to
+// 3.5 TB/s of HBM traffic, at the 1 kW cap) — not shared memory — bound the exact mode.
 // Shared memory carries only the weight tiles and the outgoing rows:
 //   * the transform warps read the fp32 map straight from global memory — cells are the contiguous
 //     dimension, so a warp's load of one channel is one 128-byte line — one k-block ahead in registers
@@ -1450,8 +1455,9 @@ int launch_project_n(const float* fmap, long long m_total, int E, int hw, int k,
     // tests): staged = bf16 operand tiles in shared memory, tmem = A operand in tensor memory,
     // reg = register-path loads without raw staging.  Read per call (a getenv, not on any hot loop).
     const char* mode_env = getenv("ISX_PROJECT_MODE");
+    // default: the staged kernel where the map's shape allows TMA boxes, else K3d (any shape)
     const int mode = (mode_env && mode_env[0] == 't') ? 0 : (mode_env && mode_env[0] == 'r') ? 2
-                     : (mode_env && mode_env[0] == 's') ? 1 : 3;  // default: direct (K3d)
+                     : (mode_env && mode_env[0] == 'd') ? 3 : (mode_env && mode_env[0] == 's') ? 1 : (p.prefetch ? 1 : 3);
     if (p.prefetch && fast) {
       p.fast = 1;
       return launch_project_kernel<-1, 2>(twf, twl, tx, p, grid, stream);
