@@ -229,7 +229,7 @@ def workload_config(n_gpus: int) -> dict:
                     + (f" row-sharded over {n_gpus} GPUs" if n_gpus > 1 else " on 1 GPU")
                     + f", {Q} bf16 queries (BASELINE.json configs[1])",
         "store_rows": N_STORE, "dim": D, "queries": Q, "k": K,
-        "parallelism": f"row-sharded store x{n_gpus}, replicated queries, one all-gather + merge" if n_gpus > 1 else "single GPU",
+        "parallelism": f"row-sharded store x{n_gpus}, replicated queries, one gather of packed records + merge" if n_gpus > 1 else "single GPU",
         "l2": "inputs larger than L2 (store shard >= 320 MB vs 126 MB L2); no explicit flush",
     }
 
@@ -378,10 +378,6 @@ def timed_steps(fn, steps: int, warmup: int, dist_on: bool):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total = float(t.item())
     return total / steps
-
-
-def _agg(dist_on: bool, sec: float) -> float:
-    return sec  # timed_steps already returns the max over ranks when dist_on
 
 
 def _hbm(algo_bytes: float, sec: float, peaks: dict) -> dict:
@@ -715,7 +711,7 @@ def run_b200(args) -> None:
     import torch.distributed as dist
 
     from imagescry_b200 import _lib
-    from imagescry_b200.search import EmbeddingStore, ShardedEmbeddingStore, gather_records, merge_topk_packed, row_rnorm, shard_range
+    from imagescry_b200.search import EmbeddingStore, ShardedEmbeddingStore, row_rnorm, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -728,10 +724,14 @@ def run_b200(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist_on = world > 1
+    real_stdout = None
     if dist_on:
-        # stdout carries exactly one JSON line: NCCL's own log (whatever level the caller chose with
-        # NCCL_DEBUG, left untouched) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly one JSON line.  NCCL prints its version banner (and, at NCCL_DEBUG=INFO,
+        # its whole log) with printf on fd 1; NCCL_DEBUG is left as the caller set it and fd 1 is pointed
+        # at stderr for the run instead — the JSON line is written to the saved descriptor at the end
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     peaks = load_peaks()
@@ -752,11 +752,12 @@ def run_b200(args) -> None:
                 store_rows[lo - b:hi - b] = chunk[lo - s:hi - s]
             del chunk
     queries = device_randn_bf16(Q, D, 4321, dev)
-    store = EmbeddingStore(store_rows, index_base=b)
     sharded = None
     if dist_on:
-        sharded = ShardedEmbeddingStore.__new__(ShardedEmbeddingStore)
-        sharded.group, sharded.world_size, sharded.rank, sharded.local, sharded.total_rows = None, world, rank, store, N_STORE
+        sharded = ShardedEmbeddingStore(store_rows, total_rows=N_STORE)
+        store = sharded.local
+    else:
+        store = EmbeddingStore(store_rows, index_base=b)
     torch.cuda.synchronize()
 
     lib = _lib.load()
@@ -764,11 +765,10 @@ def run_b200(args) -> None:
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
     scores = torch.empty((Q, K), dtype=torch.float32, device=dev)
     idx = torch.empty((Q, K), dtype=torch.int32, device=dev)
-    records = torch.empty((Q, K), dtype=torch.int64, device=dev)
     ev_pairs: list = []
 
     def search_local(q_dev, record: bool):
-        """row norms of the queries + the fused search of this rank's rows; N > 1: packed records"""
+        """N = 1: row norms of the queries + the fused search, straight through the C ABI"""
         qr = row_rnorm(q_dev)
         stream = torch.cuda.current_stream(dev)
         if record:
@@ -777,8 +777,7 @@ def run_b200(args) -> None:
             e0.record(stream)
         rc = lib.isx_knn_search_ex(
             store.embeddings.data_ptr(), store.rnorm.data_ptr(), len(store), q_dev.data_ptr(), qr.data_ptr(), Q, D, K,
-            store.index_base, 0, _lib.KNN_PACKED if dist_on else 0, records.data_ptr() if dist_on else scores.data_ptr(),
-            None if dist_on else idx.data_ptr(), ws.data_ptr(), ws.numel(), stream.cuda_stream,
+            store.index_base, 0, 0, scores.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(), stream.cuda_stream,
         )
         _lib.check(rc, "isx_knn_search_ex")
         if record:
@@ -786,13 +785,17 @@ def run_b200(args) -> None:
             ev_pairs.append((e0, e1))
 
     def step(q_dev=queries, record=True):
-        search_local(q_dev, record)
         if dist_on:
-            return merge_topk_packed(gather_records(records), K)  # ONE all-gather of packed (score, index) records
+            # row norms + fused search whose finalising pass stores the packed records into every rank's
+            # gather buffer over NVLink (symmetric memory) + device barrier + merge; NCCL all-gather of
+            # the packed records where peer mapping is unavailable
+            sharded._event_sink = ev_pairs if record else None
+            return sharded.search_raw(q_dev, K)
+        search_local(q_dev, record)
         return scores, idx
 
-    # kernels of mine per step: row_rnorm + search + finalise (+ cross-rank merge); the two memsets and
-    # the NCCL all-gather are library work
+    # kernels of mine per step: row_rnorm + search + finalise(+scatter) (+ cross-rank merge); the two
+    # memsets, the symmetric-memory barrier / NCCL all-gather are library work
     launches = 3 + (1 if dist_on else 0)
 
     # Pre-heat: the part is power-limited (sw_power_cap); its SM clock settles about two seconds into a
@@ -835,6 +838,7 @@ def run_b200(args) -> None:
     def e2e_step():
         if dist_on:
             # every rank uploads 1/N of the query rows; one all-gather over NVLink replicates them
+            sharded._event_sink = None
             s, i = sharded.search_raw(sharded.replicate_queries(q_host), K)
         else:
             q_stage.copy_(q_host, non_blocking=True)
@@ -848,7 +852,7 @@ def run_b200(args) -> None:
         "value": Q / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": q_host.numel() * 2,
         "d2h_bytes_per_step": out_s_host.numel() * 4 + out_i_host.numel() * 4, "ms_per_step": sec_e2e * 1e3,
         "api": ("ShardedEmbeddingStore.search_raw: each rank uploads 1/N of the pinned host queries, all-gather over NVLink, local "
-                "search, ONE all-gather of packed records + merge" if dist_on
+                f"search, gather of packed records ({sharded.gather_path}) + merge" if dist_on
                 else "EmbeddingStore.search_raw(queries, k) on a device-resident store; queries from pinned host memory"),
     }
 
@@ -912,13 +916,19 @@ def run_b200(args) -> None:
             "dtype": "bf16", "data": "synthetic", "config": dict(workload_config(world), preheat_s=args.preheat, preheat_steps=heat_steps),
             "clocks": clock_summary, "e2e": e2e, "gpu_launches": launches * args.steps, "roofline": roofline,
         }
+        if dist_on:
+            line["config"]["gather"] = sharded.gather_path
         if verify:
             line["verify"] = verify
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         if extra:
             line["extra"] = extra
-        print(json.dumps(line), flush=True)
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()

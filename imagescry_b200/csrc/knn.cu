@@ -975,6 +975,16 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 // ------------------------------------------------------------------------------------------
 // K5: merge g sorted-or-not partial lists per query into the final top-k.  One warp per query.
 // ------------------------------------------------------------------------------------------
+// Finalising straight into peer memory: the packed records of this rank are stored into slot
+// `slot_off` of every peer's gather buffer over NVLink (peer-mapped device pointers), so that
+// "finalise + all-gather" is one kernel and the ranks only need a barrier before they merge.
+constexpr int kMaxPeers = 16;
+struct PeerOut {
+  uint2* ptr[kMaxPeers];
+  int n;
+  long long slot_off;  // in records
+};
+
 // Partial lists come either as two arrays (scores fp32, idx int32) or — idx == nullptr — as packed
 // 8-byte records {fp32 score, int32 index} (what one all-gather moves); the result likewise
 // (out_idx == nullptr: packed records at out_scores).
@@ -982,7 +992,7 @@ template <int CAP>
 __global__ void __launch_bounds__(128)
 topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx, int g, int q, int k,
                   const float* __restrict__ query_scale, float* __restrict__ out_scores,
-                  int32_t* __restrict__ out_idx) {
+                  int32_t* __restrict__ out_idx, const PeerOut peers) {
   constexpr int E = CAP / 32;
   const int lane = threadIdx.x & 31;
   const int query = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1032,20 +1042,28 @@ topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
       const float sv = have ? s[e] : -INFINITY;
       const int iv = have ? id[e] : -1;
       const size_t o = static_cast<size_t>(query) * k + pos;
-      if (out_idx) { out_scores[o] = sv; out_idx[o] = iv; }
-      else reinterpret_cast<uint2*>(out_scores)[o] = make_uint2(__float_as_uint(sv), static_cast<uint32_t>(iv));
+      const uint2 rec2 = make_uint2(__float_as_uint(sv), static_cast<uint32_t>(iv));
+      if (peers.n > 0) {
+#pragma unroll 1
+        for (int pi = 0; pi < peers.n; ++pi) peers.ptr[pi][peers.slot_off + o] = rec2;
+      } else if (out_idx) { out_scores[o] = sv; out_idx[o] = iv; }
+      else reinterpret_cast<uint2*>(out_scores)[o] = rec2;
     }
   }
 }
 
 int launch_merge(const float* scores, const int32_t* idx, int g, int q, int k, const float* query_scale,
-                 float* out_scores, int32_t* out_idx, cudaStream_t stream) {
+                 float* out_scores, int32_t* out_idx, cudaStream_t stream, const PeerOut* peers_in = nullptr) {
   const int warps_per_block = 4;
   const int blocks = (q + warps_per_block - 1) / warps_per_block;
+  PeerOut peers;
+  peers.n = 0;
+  peers.slot_off = 0;
+  if (peers_in) peers = *peers_in;
   if (k <= 32)
-    topk_merge_kernel<64><<<blocks, 128, 0, stream>>>(scores, idx, g, q, k, query_scale, out_scores, out_idx);
+    topk_merge_kernel<64><<<blocks, 128, 0, stream>>>(scores, idx, g, q, k, query_scale, out_scores, out_idx, peers);
   else
-    topk_merge_kernel<256><<<blocks, 128, 0, stream>>>(scores, idx, g, q, k, query_scale, out_scores, out_idx);
+    topk_merge_kernel<256><<<blocks, 128, 0, stream>>>(scores, idx, g, q, k, query_scale, out_scores, out_idx, peers);
   ISX_CHECK_CUDA(cudaGetLastError());
   return ISX_OK;
 }
@@ -1161,11 +1179,10 @@ size_t isx_knn_workspace_bytes(int64_t n, int q, int d, int k) {
   return knn_workspace(sms, q, k).total;
 }
 
-int isx_knn_search_ex(const void* store, const float* store_rnorm, int64_t n, const void* queries,
-                      const float* query_rnorm, int q, int d, int k, int64_t index_base,
-                      int64_t query_index_base, int flags, float* out_scores, int32_t* out_idx,
-                      void* workspace, size_t workspace_bytes, isx_stream_t stream_) {
-  const char* fn = "isx_knn_search_ex";
+static int knn_search_impl(const char* fn, const void* store, const float* store_rnorm, int64_t n, const void* queries,
+                           const float* query_rnorm, int q, int d, int k, int64_t index_base,
+                           int64_t query_index_base, int flags, float* out_scores, int32_t* out_idx,
+                           void* workspace, size_t workspace_bytes, isx_stream_t stream_, const PeerOut* peers) {
   const bool cont = (flags & ISX_KNN_CONTINUE) != 0, finalize = (flags & ISX_KNN_NO_FINALIZE) == 0;
   const bool packed = (flags & ISX_KNN_PACKED) != 0, no_self = (flags & ISX_KNN_EXCLUDE_SELF) != 0;
   ISX_REQUIRE((flags & ~(ISX_KNN_CONTINUE | ISX_KNN_NO_FINALIZE | ISX_KNN_EXCLUDE_SELF | ISX_KNN_PACKED)) == 0,
@@ -1177,7 +1194,7 @@ int isx_knn_search_ex(const void* store, const float* store_rnorm, int64_t n, co
   ISX_REQUIRE(n < (1ll << 31) - BN, "%s: at most 2^31 store rows per call (n=%lld); shard the store", fn, (long long)n);
   ISX_REQUIRE(index_base >= 0 && index_base + n < (1ll << 31), "%s: index_base + n must fit in int32", fn);
   ISX_REQUIRE(queries && query_rnorm, "%s: null pointer", fn);
-  ISX_REQUIRE(!finalize || (out_scores && (packed || out_idx)), "%s: null output pointer", fn);
+  ISX_REQUIRE(!finalize || peers || (out_scores && (packed || out_idx)), "%s: null output pointer", fn);
   ISX_REQUIRE(!no_self || (query_index_base >= 0 && query_index_base + q < (1ll << 31)),
               "%s: query_index_base + q must fit in int32 (got %lld)", fn, (long long)query_index_base);
   ISX_REQUIRE((reinterpret_cast<uintptr_t>(queries) & 15u) == 0 && (reinterpret_cast<uintptr_t>(store) & 15u) == 0,
@@ -1200,7 +1217,7 @@ int isx_knn_search_ex(const void* store, const float* store_rnorm, int64_t n, co
   if (n == 0) {
     // nothing to search in this block: the lists stay as they are
     if (!finalize) return ISX_OK;
-    return launch_merge(run_scores, run_idx, 1, q, k, query_rnorm, out_scores, packed ? nullptr : out_idx, stream);
+    return launch_merge(run_scores, run_idx, 1, q, k, query_rnorm, out_scores, packed ? nullptr : out_idx, stream, peers);
   }
   ISX_REQUIRE(store && store_rnorm, "%s: null store pointer", fn);
   const int ncta = (sms >= 2) ? knn_ncta(q) : 1;
@@ -1283,7 +1300,36 @@ int isx_knn_search_ex(const void* store, const float* store_rnorm, int64_t n, co
   if (!finalize) return ISX_OK;
   // finalize: scale the running lists by the queries' inverse norms, order by the final
   // (score desc, row asc); packed: one 8-byte record per hit (what a single all-gather moves)
-  return launch_merge(p.run_scores, p.run_idx, 1, q, k, query_rnorm, out_scores, packed ? nullptr : out_idx, stream);
+  return launch_merge(p.run_scores, p.run_idx, 1, q, k, query_rnorm, out_scores, packed ? nullptr : out_idx, stream, peers);
+}
+
+int isx_knn_search_ex(const void* store, const float* store_rnorm, int64_t n, const void* queries,
+                      const float* query_rnorm, int q, int d, int k, int64_t index_base,
+                      int64_t query_index_base, int flags, float* out_scores, int32_t* out_idx,
+                      void* workspace, size_t workspace_bytes, isx_stream_t stream) {
+  return knn_search_impl("isx_knn_search_ex", store, store_rnorm, n, queries, query_rnorm, q, d, k, index_base,
+                         query_index_base, flags, out_scores, out_idx, workspace, workspace_bytes, stream, nullptr);
+}
+
+int isx_knn_search_scatter(const void* store, const float* store_rnorm, int64_t n, const void* queries,
+                           const float* query_rnorm, int q, int d, int k, int64_t index_base,
+                           int64_t query_index_base, int flags, void* const* peer_bufs, int n_peers, int slot,
+                           void* workspace, size_t workspace_bytes, isx_stream_t stream) {
+  const char* fn = "isx_knn_search_scatter";
+  ISX_REQUIRE(peer_bufs != nullptr && n_peers >= 1 && n_peers <= kMaxPeers, "%s: need 1..%d peer buffers (got %d)", fn,
+              kMaxPeers, n_peers);
+  ISX_REQUIRE(slot >= 0 && slot < n_peers, "%s: slot %d outside [0, %d)", fn, slot, n_peers);
+  ISX_REQUIRE((flags & (ISX_KNN_NO_FINALIZE | ISX_KNN_PACKED)) == 0, "%s: the scatter is the finalising pass (flags 0x%x)", fn, flags);
+  PeerOut peers;
+  peers.n = n_peers;
+  peers.slot_off = static_cast<long long>(slot) * q * k;
+  for (int i = 0; i < n_peers; ++i) {
+    ISX_REQUIRE(peer_bufs[i] != nullptr && (reinterpret_cast<uintptr_t>(peer_bufs[i]) & 7u) == 0,
+                "%s: peer buffer %d is null or not 8-byte aligned", fn, i);
+    peers.ptr[i] = static_cast<uint2*>(peer_bufs[i]);
+  }
+  return knn_search_impl(fn, store, store_rnorm, n, queries, query_rnorm, q, d, k, index_base, query_index_base, flags,
+                         nullptr, nullptr, workspace, workspace_bytes, stream, &peers);
 }
 
 int isx_knn_search(const void* store, const float* store_rnorm, int64_t n, const void* queries,

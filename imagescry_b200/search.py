@@ -308,11 +308,100 @@ class ShardedEmbeddingStore:
         self.total_rows = total_rows
         self.local = EmbeddingStore(local_embeddings, index_base=index_base)
 
+    # ------------------------------------------------------------------ gather over peer memory
+    def _peer_buffers(self, nq: int, k: int):
+        """Symmetric (peer-mapped) gather buffers for Q×k results: [2 parities][G][Q][k] packed records
+        on every rank, exchanged once through torch's symmetric-memory rendezvous.  With them the
+        search's finalising pass stores this rank's records straight into every peer's buffer over
+        NVLink (`isx_knn_search_scatter`): finalise + all-gather is ONE kernel of ours, followed by a
+        device-side barrier.  Returns None when peer mapping is unavailable (gloo / no NVLink P2P /
+        ISX_PEER_GATHER=0): the NCCL all-gather of `gather_records` is used instead."""
+        import os
+
+        import torch.distributed as dist
+
+        key = (nq, k)
+        cache = self.__dict__.setdefault("_peer_cache", {})
+        if key in cache:
+            return cache[key]
+        entry = None
+        if os.environ.get("ISX_PEER_GATHER", "1") != "0" and self.world_size <= 16 and self.local.device.type == "cuda":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                group = self.group if self.group is not None else dist.group.WORLD
+                buf = symm_mem.empty((2, self.world_size, nq, k), dtype=torch.int64, device=self.local.device)
+                hdl = symm_mem.rendezvous(buf, group)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                if len(ptrs) == self.world_size and all(ptrs):
+                    entry = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "step": 0}
+            except Exception as ex:  # no peer mapping on this system: NCCL carries the gather
+                import sys
+
+                print(f"imagescry_b200: symmetric-memory gather unavailable ({ex!r}); using the NCCL all-gather", file=sys.stderr)
+        # every rank must take the same path
+        flag = torch.tensor([1 if entry is not None else 0], dtype=torch.int32, device=self.local.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            entry = None
+        cache[key] = entry
+        return entry
+
+    @property
+    def gather_path(self) -> str:
+        """"peer-store" once a search has used the symmetric-memory path, else "nccl"."""
+        return "peer-store" if any(v is not None for v in self.__dict__.get("_peer_cache", {}).values()) else "nccl"
+
     def search_raw(self, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
-        """(scores fp32 Q×k, GLOBAL indices int32 Q×k): local fused search → ONE all-gather of packed
-        (score, index) records → merge."""
-        rec = self.local.search_packed(queries, k)
-        return merge_topk_packed(gather_records(rec, self.group), k)
+        """(scores fp32 Q×k, GLOBAL indices int32 Q×k): local fused search whose finalising pass stores
+        the packed (score, index) records into every rank's gather buffer over NVLink, a device-side
+        barrier, merge.  Without peer-mapped memory: local search → ONE NCCL all-gather of the packed
+        records → merge."""
+        import ctypes
+
+        q = self.local._queries(queries)
+        self.local._check_k(k)
+        nq = q.shape[0]
+        peer = self._peer_buffers(nq, k) if nq else None
+        if peer is None:
+            sink = self.__dict__.get("_event_sink")
+            if sink is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                qr0 = row_rnorm(q)
+                e0.record()
+                rec = self.local.search_packed(q, k, query_rnorm=qr0)
+                e1.record()
+                sink.append((e0, e1))
+            else:
+                rec = self.local.search_packed(q, k)
+            return merge_topk_packed(gather_records(rec, self.group), k)
+        lib = _lib.load()
+        st = self.local
+        qr = row_rnorm(q)
+        parity = peer["step"] & 1
+        peer["step"] += 1
+        stride = self.world_size * nq * k * 8  # bytes of one parity's [G][Q][k] block
+        arr = (ctypes.c_void_p * self.world_size)(*[p + parity * stride for p in peer["ptrs"]])
+        ws_bytes = max(int(lib.isx_knn_workspace_bytes(max(len(st), 1), nq, st.dim, k)), 256)
+        ws = st._ws(ws_bytes)
+        sink = self.__dict__.get("_event_sink")
+        with _lib.on_device(st.embeddings, q, qr, ws) as stream:
+            if sink is not None:  # bench.py times the fused search + scatter kernel with CUDA events
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            rc = lib.isx_knn_search_scatter(
+                st.embeddings.data_ptr(), st.rnorm.data_ptr(), len(st), q.data_ptr(), qr.data_ptr(), nq, st.dim, k,
+                st.index_base, 0, 0, arr, self.world_size, self.rank, ws.data_ptr(), ws.numel(), stream,
+            )
+            _lib.check(rc, "isx_knn_search_scatter")
+            if sink is not None:
+                e1.record()
+                sink.append((e0, e1))
+            # every rank's stores have landed once all ranks passed this barrier; the buffer of this
+            # parity is rewritten two searches later, after every rank has passed the NEXT barrier,
+            # i.e. after its merge of this one (stream order)
+            peer["hdl"].barrier(channel=parity)
+        return merge_topk_packed(peer["buf"][parity], k)
 
     def search(self, queries: Tensor, k: int) -> tuple[Tensor, Tensor]:
         s, i = self.search_raw(queries, k)

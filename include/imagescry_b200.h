@@ -198,6 +198,17 @@ int isx_knn_search_ex(const void* store, const float* store_rnorm, int64_t n, co
                       int64_t query_index_base, int flags, float* out_scores, int32_t* out_idx,
                       void* workspace, size_t workspace_bytes, isx_stream_t stream);
 
+/* Row-sharded search whose finalising pass IS the gather: this rank's q x k packed records are stored
+ * straight into slot `slot` of every rank's g x q x k gather buffer over NVLink.  peer_bufs is a HOST
+ * array of n_peers device pointers (peer-mapped memory, e.g. torch symmetric memory / cuMem IPC; entry
+ * `slot` is this rank's own buffer).  No collective library call is involved; the caller runs a
+ * cross-rank barrier before isx_topk_merge_packed reads its buffer.  flags: ISX_KNN_CONTINUE and
+ * ISX_KNN_EXCLUDE_SELF as above. */
+int isx_knn_search_scatter(const void* store, const float* store_rnorm, int64_t n, const void* queries,
+                           const float* query_rnorm, int q, int d, int k, int64_t index_base,
+                           int64_t query_index_base, int flags, void* const* peer_bufs, int n_peers, int slot,
+                           void* workspace, size_t workspace_bytes, isx_stream_t stream);
+
 /* Merge g partial results (scores, idx: g x q x k, e.g. the NCCL all-gather of every shard's
  * local top-k) into q x k with the same ordering.  idx < 0 marks padding. */
 int isx_topk_merge(const float* scores, const int32_t* idx, int g, int q, int k, float* out_scores,

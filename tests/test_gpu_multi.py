@@ -45,6 +45,18 @@ for k in (10, 100):
     assert torch.equal(i, fi) and torch.allclose(s, fs, atol=1e-6), (rank, k)
     check(store, queries, k, s, i)   # every index mismatch justified by a sub-tolerance score gap
     assert i[0, :2].tolist() == [7, 29000]
+# the gather over peer memory (finalise + scatter in one kernel, symmetric-memory barrier) and the NCCL
+# all-gather of packed records give the same answer
+print("gather path:", sharded.gather_path, flush=True)
+os.environ["ISX_PEER_GATHER"] = "0"
+nccl_sharded = ShardedEmbeddingStore(torch.from_numpy(store[b:e]).cuda(), total_rows=n)
+for k in (10, 100):
+    for rep in range(3):   # both parities of the peer buffers
+        s1, i1 = sharded.search_raw(qd, k)
+        s2, i2 = nccl_sharded.search_raw(qd, k)
+        assert torch.equal(i1, i2) and torch.equal(s1, s2), (rank, k, rep)
+assert nccl_sharded.gather_path == "nccl"
+del os.environ["ISX_PEER_GATHER"]
 # all-pairs graph over the sharded store (config 5): queries sharded, store rotated through the
 # all-gather, running lists kept in the kernel workspace == the single-GPU graph == the oracle
 gn = 5003
