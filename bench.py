@@ -829,6 +829,16 @@ def run_b200(args) -> None:
         "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
     }
 
+    if dist_on:
+        # the ranks meet at a barrier every step, so a step lasts as long as its slowest rank's kernel:
+        # report every rank's own average kernel time next to rank 0's
+        t = torch.tensor([k_ms], dtype=torch.float64, device=dev)
+        allk = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allk, t)
+        roofline["kernel_ms_per_rank"] = [float(x.item()) for x in allk]
+        roofline["note"] = ("ms_per_step - kernel_ms = query norms + barrier + merge + the wait for the slowest rank of every step "
+                            "(per-rank kernel times differ with each GPU's clock)")
+
     # ---- e2e: pinned host queries -> H2D -> search -> D2H of the result, through the public API
     q_host = queries.cpu().pin_memory()
     out_s_host = torch.empty((Q, K), dtype=torch.float32).pin_memory()
