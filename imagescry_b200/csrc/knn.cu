@@ -881,68 +881,103 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
         ISX_PROF_END1(13);
       } else {
-        while (todo) {
-          const int rr = __ffs(todo) - 1;
-          todo &= todo - 1;
+        // 256-entry buffers (k > 16), the same phase structure: the per-row chain used to be
+        // sort -> lock spin -> fence -> running-list loads -> merge -> stores -> fence -> unlock, ~18 k cycles
+        // a row and 32 rows in sequence (measured at k = 100: 1357 cycles per tile, 8.6 % of the kernel, with
+        // the MMAs stalled behind two full accumulator stages meanwhile).  Now
+        //  A  every row is sorted first; its best k stay in the row's buffer (global memory, L2);
+        //  B  every lane TRIES the lock of its own row once;
+        //  C  the rows whose lock was taken are merged one after the other (bitonic merge with the
+        //     running list) without any lock or fence latency in between;
+        //  D  one fence, then every lane publishes its row's bound and releases its lock.
+        {
+          uint32_t t = todo;
+          while (t) {
+            const int rr = __ffs(t) - 1;
+            t &= t - 1;
+            __syncwarp();
+            const int c = __shfl_sync(kFullMask, cnt, rr);
+            float nthr;
+            int ncnt;
+            prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr, ncnt,
+                           s_reg, i_reg);
+            if (lane == rr) cnt = ncnt;
+          }
           __syncwarp();
-          const int c = __shfl_sync(kFullMask, cnt, rr);
-          const int qr = m0 + ew * 32 + rr;
-          float nthr;
-          int ncnt;
-          prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr, ncnt,
-                         s_reg, i_reg);
-          if (qr < p.q && ncnt > 0) {  // warp-uniform
+        }
+        ISX_PROF_COUNT(14, __popc(todo));
+        uint32_t pending = todo & __ballot_sync(kFullMask, cnt > 0);
+        uint64_t t0 = 0;
+        while (pending) {
+          const bool mine = (pending >> lane) & 1u;
+          const bool got = mine && atomicCAS(p.run_lock + qrow, 0u, 1u) == 0u;
+          uint32_t gotm = __ballot_sync(kFullMask, got);
+          if (gotm == 0) {
+            __nanosleep(128);
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > ISX_MBAR_TIMEOUT_NS) {
+              if (lane == 0) printf("isx: knn_search_kernel: running-list locks timed out (rows %08x of block %d)\n", pending, m0);
+              __trap();
+            }
+            continue;
+          }
+          pending &= ~gotm;
+          __threadfence();
+          float kth_mine = -INFINITY;
+          bool kth_valid_mine = false;
+          while (gotm) {
+            const int rr = __ffs(gotm) - 1;
+            gotm &= gotm - 1;
+            const int c = __shfl_sync(kFullMask, cnt, rr);
+            const int qr = m0 + ew * 32 + rr;
+            const uint2* buf = warp_buf + static_cast<size_t>(rr) * cand_stride;
             float* gs = p.run_scores + static_cast<size_t>(qr) * p.k;
             int32_t* gi = p.run_idx + static_cast<size_t>(qr) * p.k;
-            if (lane == 0) {
-              uint64_t t0 = 0;
-              while (atomicCAS(p.run_lock + qr, 0u, 1u) != 0u) {
-                __nanosleep(64);
-                const uint64_t now = global_timer_ns();
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > ISX_MBAR_TIMEOUT_NS) {
-                  printf("isx: knn_search_kernel: running-list lock of query %d timed out\n", qr);
-                  __trap();
-                }
-              }
-              __threadfence();
-            }
-            __syncwarp();
-            // bitonic input: slots [0, k) this item's best (sorted descending), the running list
+            // bitonic input: slots [0, c) this item's best (sorted descending, c <= k), the running list
             // reversed at the top (slot CAP-1-j = its j-th best), (-inf, none) in between
-  #pragma unroll
+#pragma unroll
             for (int e = 0; e < E; ++e) {
               const int i = e * 32 + lane;
-              if (i >= ncnt) { s_reg[e] = -INFINITY; i_reg[e] = INT_MAX; }
+              float sv = -INFINITY;
+              int iv = INT_MAX;
+              if (i < c) {
+                const uint2 v = buf[i];
+                sv = __uint_as_float(v.x);
+                iv = static_cast<int>(v.y);
+              }
               const int j = CAP - 1 - i;
               if (j < p.k) {
                 const int id = __ldcg(gi + j);
                 const float sc = __ldcg(gs + j);
-                if (id >= 0) { s_reg[e] = sc; i_reg[e] = id; }
+                if (id >= 0) { sv = sc; iv = id; }
               }
+              s_reg[e] = sv;
+              i_reg[e] = iv;
             }
             warp_merge_desc<E>(s_reg, i_reg);
             float kth = -INFINITY;
             bool kth_valid = false;
-  #pragma unroll
+#pragma unroll
             for (int e = 0; e < E; ++e) {
               const int i = e * 32 + lane;
               if (i < p.k) {
-                const bool have = i_reg[e] != INT_MAX;
                 gs[i] = s_reg[e];
-                gi[i] = have ? i_reg[e] : -1;
+                gi[i] = (i_reg[e] != INT_MAX) ? i_reg[e] : -1;
               }
               const float cs = __shfl_sync(kFullMask, s_reg[e], (p.k - 1) & 31);
               const int ci = __shfl_sync(kFullMask, i_reg[e], (p.k - 1) & 31);
               if (e == ((p.k - 1) >> 5)) { kth = cs; kth_valid = ci != INT_MAX; }
             }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-              if (kth_valid) atomicMax(p.thr_shared + qr, thr_encode(kth));
-              atomicExch(p.run_lock + qr, 0u);
-            }
+            if (lane == rr) { kth_mine = kth; kth_valid_mine = kth_valid; }
           }
+          __threadfence();
+          __syncwarp();
+          if (got) {
+            if (kth_valid_mine) atomicMax(p.thr_shared + qrow, thr_encode(kth_mine));
+            atomicExch(p.run_lock + qrow, 0u);
+          }
+          ISX_PROF_COUNT(15, 1);
         }
       }
       __syncwarp();
