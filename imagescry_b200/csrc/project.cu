@@ -847,7 +847,7 @@ l2norm_project_tmem_kernel(const __grid_constant__ CUtensorMap tmap_whi, const _
 // Shared memory carries only the weight tiles and the outgoing rows:
 //   * the transform warps read the fp32 map straight from global memory — cells are the contiguous
 //     dimension, so a warp's load of one channel is one 128-byte line — one k-block ahead in registers
-//     (32 KB of loads in flight per SM), accumulate the cells' sums of squares, split to bf16 hi/lo and
+//     (two register buffers: 32-64 KB of loads in flight per SM), accumulate the sums of squares, split to bf16 hi/lo and
 //     write the A operand with tcgen05.st into TENSOR MEMORY (4 stages x 64 columns next to the
 //     256-column accumulator); the MMAs take A from there (TS form);
 //   * warp 3 asks the TMA unit to pull the boxes of the map into L2 a few k-blocks ahead;
@@ -1031,37 +1031,42 @@ l2norm_project_direct_kernel(const __grid_constant__ CUtensorMap tmap_whi, const
       const int f0 = ld_kb * PK + fg * 16;
       const float* src = ld_base + static_cast<long long>(f0) * hw;
       const bool live = ld_valid && f0 < p.E;
+      if (live) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = live ? ld_f32(src + i * hw) : 0.f;
+        for (int i = 0; i < 16; ++i) { x[i] = ld_f32(src); src += hw; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = 0.f;
+      }
       if (++ld_kb == num_kb) { ld_kb = 0; seek(++ld_tile); }
     };
     float ss = 0.f;
     uint32_t as = 0, aph = 0, sst = 0, ssph = 0;
     int pr_kb = 0;
-    float x[16];
-    if (total_seq > 0) load_block(x);
-    for (long long seq = 0; seq < total_seq; ++seq) {
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float a = x[2 * i], b = x[2 * i + 1];
-        ss = fmaf(a, a, ss);
-        ss = fmaf(b, b, ss);
-        // hi = x truncated to bf16 (a mask); lo = RN_bf16(x - hi): |x - hi - lo| <= 2^-16 |x|
-        const uint32_t ab = __float_as_uint(a), bb = __float_as_uint(b);
-        hi[i] = __byte_perm(ab, bb, 0x7632);
-        const float la = a - __uint_as_float(ab & 0xFFFF0000u);
-        const float lb = b - __uint_as_float(bb & 0xFFFF0000u);
-        const __nv_bfloat162 l2 = __floats2bfloat162_rn(la, lb);
-        lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
-      }
-      // the next k-block's loads go out now (x is free) and fly while this one is handed to the MMA;
-      // the other 15 transform warps of the SM cover the rest of their latency
-      if (seq + 1 < total_seq) load_block(x);
+    // convert one k-block's 16 features (two halves of 8: four packed columns of hi and of lo each)
+    // and hand it to the MMA
+    auto process = [&](float (&x)[16]) {
       mbar_wait(&a_empty[as], aph ^ 1);
       tc_fence_after();
-      tmem_st_32x8(t_row + as * 64, hi);
-      tmem_st_32x8(t_row + as * 64 + 32, lo);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = x[8 * h + 2 * i], b = x[8 * h + 2 * i + 1];
+          ss = fmaf(a, a, ss);
+          ss = fmaf(b, b, ss);
+          // hi = x truncated to bf16 (a mask); lo = RN_bf16(x - hi): |x - hi - lo| <= 2^-16 |x|
+          const uint32_t ab = __float_as_uint(a), bb = __float_as_uint(b);
+          hi[i] = __byte_perm(ab, bb, 0x7632);
+          const float la = a - __uint_as_float(ab & 0xFFFF0000u);
+          const float lb = b - __uint_as_float(bb & 0xFFFF0000u);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(la, lb);
+          lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        tmem_st_32x4(t_row + as * 64 + 4 * h, hi);
+        tmem_st_32x4(t_row + as * 64 + 32 + 4 * h, lo);
+      }
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -1076,6 +1081,18 @@ l2norm_project_direct_kernel(const __grid_constant__ CUtensorMap tmap_whi, const
         if (lane == 0) mbar_arrive(&ss_full[sst]);
         ss = 0.f;
         if (++sst == 2) { sst = 0; ssph ^= 1; }
+      }
+    };
+    // two register buffers: the loads of k-block n + 1 are in flight while k-block n waits for its
+    // operand stage, is converted and stored — a whole k-block period of latency cover per warp
+    float xa[16], xb[16];
+    if (total_seq > 0) load_block(xa);
+    for (long long seq = 0; seq < total_seq; seq += 2) {
+      if (seq + 1 < total_seq) load_block(xb);
+      process(xa);
+      if (seq + 1 < total_seq) {
+        if (seq + 2 < total_seq) load_block(xa);
+        process(xb);
       }
     }
   } else if (warp >= 4 && warp < 8) {
