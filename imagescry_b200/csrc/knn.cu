@@ -891,16 +891,58 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         //     running list) without any lock or fence latency in between;
         //  D  one fence, then every lane publishes its row's bound and releases its lock.
         {
+          // A: a row's buffer holds everything that beat the row's threshold when it was appended; by
+          // now the grid's bound for the query (the k-th best of every finished item's rows) is usually
+          // higher.  Entries below it can never reach the final top-k: they are dropped first, and only
+          // the survivors (a few dozen of up to 256, k / i of them for the i-th item of a query) are
+          // sorted, in the smallest network that holds them — the 256-entry sort was 17 k cycles a row.
           uint32_t t = todo;
           while (t) {
             const int rr = __ffs(t) - 1;
             t &= t - 1;
             __syncwarp();
             const int c = __shfl_sync(kFullMask, cnt, rr);
+            const int qr = m0 + ew * 32 + rr;
+            uint2* buf = warp_buf + static_cast<size_t>(rr) * cand_stride;
+            const float bound = thr_decode_below(*reinterpret_cast<const volatile uint32_t*>(p.thr_shared + qr));
+            uint2 v[E];
+            uint32_t keepm = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              const int i = e * 32 + lane;
+              v[e] = make_uint2(0u, 0u);
+              if (i < c) {
+                v[e] = buf[i];
+                if (__uint_as_float(v[e].x) > bound) keepm |= 1u << e;
+              }
+            }
+            __syncwarp();
+            int kept = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              const bool kp = (keepm >> e) & 1u;
+              const uint32_t bal = __ballot_sync(kFullMask, kp);
+              if (kp) buf[kept + __popc(bal & ((1u << lane) - 1u))] = v[e];
+              kept += __popc(bal);
+            }
+            __syncwarp();
             float nthr;
             int ncnt;
-            prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr, ncnt,
-                           s_reg, i_reg);
+            if (kept <= 32) {
+              float s1[1];
+              int i1[1];
+              prune_row<32>(buf, 0, kept, p.k, nthr, ncnt, s1, i1);
+            } else if (kept <= 64) {
+              float s2[2];
+              int i2[2];
+              prune_row<64>(buf, 0, kept, p.k, nthr, ncnt, s2, i2);
+            } else if (kept <= 128) {
+              float s4[4];
+              int i4[4];
+              prune_row<128>(buf, 0, kept, p.k, nthr, ncnt, s4, i4);
+            } else {
+              prune_row<CAP>(buf, 0, kept, p.k, nthr, ncnt, s_reg, i_reg);
+            }
             if (lane == rr) cnt = ncnt;
           }
           __syncwarp();
