@@ -433,6 +433,14 @@ __device__ __forceinline__ void tc_wait_ld_regs(uint32_t (&r)[32]) {
                : "memory");
 }
 
+__device__ __forceinline__ void tc_wait_ld_regs16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // Packed fp32 multiply (FMUL2 on sm_100): (a0, a1) *= (w0, w1), each lane rounded to nearest like FMUL.
 __device__ __forceinline__ void mul_f32x2(uint32_t& a0, uint32_t& a1, float w0, float w1) {
   uint64_t a, w, d;

@@ -840,10 +840,11 @@ l2norm_project_tmem_kernel(const __grid_constant__ CUtensorMap tmap_whi, const _
 // ------------------------------------------------------------------------------------------
 // K3d: the per-cell kernel with NO raw staging (CTA pairs; the default for map shapes the TMA boxes of
 // the staged kernel cannot express, e.g. 7 x 10 cells; ISX_PROJECT_MODE=direct forces it).
-// Measured at config 3b it runs at the staged kernel's speed (1.86 against 1.77 ms): with the raw ring
+// Measured at config 3b it runs at the staged kernel's speed (1.79 against 1.78 ms): with the raw ring
 // and the A tiles gone from shared memory the port carries 128 KB per k-block instead of 272 KB and
 // nothing got faster, which is what shows that the three tensor passes (1.15 PFLOP/s issued next to
-// 3.5 TB/s of HBM traffic, at the 1 kW cap) — not shared memory — bound the exact mode.
+// 3.6 TB/s of HBM traffic, at the 1 kW cap: 2.06 TFLOP take 1.49 ms at the sustained cuBLAS rate) — not
+// shared memory — bound the exact mode.
 // Shared memory carries only the weight tiles and the outgoing rows:
 //   * the transform warps read the fp32 map straight from global memory — cells are the contiguous
 //     dimension, so a warp's load of one channel is one 128-byte line — one k-block ahead in registers
@@ -862,7 +863,7 @@ l2norm_project_tmem_kernel(const __grid_constant__ CUtensorMap tmap_whi, const _
 //   (cells 32 (tw % 4) + lane of the tile) and features 16 (tw / 4) .. + 15 of every k-block.
 // ------------------------------------------------------------------------------------------
 struct ProjDSmem {
-  static constexpr int A_STAGES = 4, W_STAGES = 4, OUT_BUFS = 4;
+  static constexpr int A_STAGES = 4, W_STAGES = 2, OUT_BUFS = 8;  // one staging buffer per 32-column box of a tile
   static constexpr uint32_t W_PART_BYTES = (kMaxComponents / 2) * PK * 2;  // 16 KB
   static constexpr uint32_t W_STAGE_BYTES = 2 * W_PART_BYTES;              // hi + lo
   static constexpr uint32_t OUT_BUF_BYTES = PM * 32 * 4;                   // 128 rows x 32 columns fp32 = 16 KB
@@ -1100,7 +1101,7 @@ l2norm_project_direct_kernel(const __grid_constant__ CUtensorMap tmap_whi, const
     const int ew = warp - 4;  // == warp % 4: TMEM lane quarter
     const int row = ew * 32 + lane;
     const int et = threadIdx.x - 4 * 32;  // 0..127
-    uint32_t sst = 0, ssph = 0, tph = 0, ob = 0;
+    uint32_t sst = 0, ssph = 0, tph = 0;
     auto epi_bar = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
     for (long long tile = unit; tile < p.tiles; tile += num_units) {
       const long long R0 = (tile * 2 + rank) * PM;
@@ -1114,42 +1115,60 @@ l2norm_project_direct_kernel(const __grid_constant__ CUtensorMap tmap_whi, const
       __syncwarp();
       if (lane == 0) mbar_arrive(&ss_empty[sst]);
       if (++sst == 2) { sst = 0; ssph ^= 1; }
+      // the staging buffers still belong to the previous tile's TMA stores (issued a whole tile ago)
+      if (et == 0) tma_store_wait_read<0>();
+      epi_bar();
       mbar_wait(tmem_full, tph);
       tph ^= 1;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < p.k_pad; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c0, r);
-        tc_wait_ld_regs(r);
-        if (c0 + 32 >= p.k_pad) {
-          // every TMEM read of this tile has landed: the MMAs of the next tile may start
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(tmem_empty);
-        }
-        // the store that last read this staging buffer (OUT_BUFS boxes ago) must have drained it
-        if (et == 0) tma_store_wait_read<L::OUT_BUFS - 1>();
-        epi_bar();
-        uint8_t* obuf = smem + L::kOutOff + ob * L::OUT_BUF_BYTES + row * 128;
+      // Drain: the accumulator is the only one (the A stages take the other half of TMEM), so the MMAs
+      // of the next tile wait for this loop.  It does nothing but load 32 columns, scale them and park
+      // them in their own staging buffer — no barrier, no store wait inside — with the next load in
+      // flight while a box is processed; the TMA stores go out after the accumulator is released.
+      uint32_t ra[16], rb[16];
+      const int nbox = (p.k_pad + 31) >> 5;
+      const int nhalf = p.k_pad >> 4;  // 16-column pieces (k_pad is a multiple of 16)
+      auto park = [&](const uint32_t (&r)[16], int h) {
+        uint8_t* obuf = smem + L::kOutOff + (h >> 1) * L::OUT_BUF_BYTES + row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bz = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
+        for (int j = 0; j < 4; ++j) {
+          const float4 bz = __ldg(reinterpret_cast<const float4*>(p.bias + h * 16) + j);
           float4 v;
           v.x = fmaf(__uint_as_float(r[4 * j + 0]), rn, bz.x);
           v.y = fmaf(__uint_as_float(r[4 * j + 1]), rn, bz.y);
           v.z = fmaf(__uint_as_float(r[4 * j + 2]), rn, bz.z);
           v.w = fmaf(__uint_as_float(r[4 * j + 3]), rn, bz.w);
-          *reinterpret_cast<float4*>(obuf + ((j ^ (row & 7)) << 4)) = v;  // 128B swizzle
+          *reinterpret_cast<float4*>(obuf + ((((h & 1) << 2) + j) ^ (row & 7)) * 16) = v;  // 128B swizzle
         }
-        fence_proxy_async_smem();
-        epi_bar();
-        if (et == 0) {
-          tma_store_2d(&tmap_out, smem + L::kOutOff + ob * L::OUT_BUF_BYTES, c0, static_cast<int32_t>(R0));
-          tma_store_commit();
+      };
+      auto release = [&] {
+        // every TMEM read of this tile has landed: the MMAs of the next tile may start
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tmem_empty);
+      };
+      tmem_ld_32x16(taddr, ra);
+#pragma unroll 1
+      for (int h = 0; h < nhalf; h += 2) {
+        tc_wait_ld_regs16(ra);
+        const bool more = h + 1 < nhalf;
+        if (more) tmem_ld_32x16(taddr + (h + 1) * 16, rb);
+        else release();
+        park(ra, h);
+        if (more) {
+          tc_wait_ld_regs16(rb);
+          if (h + 2 < nhalf) tmem_ld_32x16(taddr + (h + 2) * 16, ra);
+          else release();
+          park(rb, h + 1);
         }
-        if (++ob == L::OUT_BUFS) ob = 0;
+      }
+      fence_proxy_async_smem();
+      epi_bar();
+      if (et == 0) {
+        for (int bx = 0; bx < nbox; ++bx)
+          tma_store_2d(&tmap_out, smem + L::kOutOff + bx * L::OUT_BUF_BYTES, bx * 32, static_cast<int32_t>(R0));
+        tma_store_commit();
       }
     }
     if (et == 0) tma_store_wait<0>();
