@@ -1033,10 +1033,29 @@ def bench_sharded_large(args, world: int, rank: int, dev, peaks: dict) -> dict:
     dist.all_reduce(t, op=dist.ReduceOp.MIN)  # every rank must hold the same number of rows
     rows = int(t.item())
     g = torch.Generator(device=dev).manual_seed(99 + rank)
-    local = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
-    for s in range(0, rows, 1 << 20):
-        ee = min(rows, s + (1 << 20))
-        local[s:ee] = torch.randn((ee - s, D), generator=g, device=dev).to(torch.bfloat16)
+    # allocate and fill; if ANY rank cannot (another tenant's memory, fragmentation) every rank halves the
+    # shard and tries again — a rank that raised alone would leave the others hanging in a collective
+    while True:
+        ok = 1
+        local = None
+        try:
+            local = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
+            for s in range(0, rows, 1 << 20):
+                ee = min(rows, s + (1 << 20))
+                local[s:ee] = torch.randn((ee - s, D), generator=g, device=dev).to(torch.bfloat16)
+        except torch.OutOfMemoryError:
+            ok = 0
+            local = None
+            torch.cuda.empty_cache()
+        t = torch.tensor([ok], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 1:
+            break
+        local = None
+        torch.cuda.empty_cache()
+        rows //= 2
+        if rows < (1 << 20):
+            return {"error": "could not allocate a shard of even 1 Mi rows on every rank"}
     store = ShardedEmbeddingStore(local, index_base=rank * rows)
     queries = device_randn_bf16(Q, D, 4321, dev)
     out = {"workload": f"{rows * world}x{D} bf16 store row-sharded over {world} GPUs ({rows} rows = {rows * D * 2 / 2**30:.1f} GiB each), {Q} queries",

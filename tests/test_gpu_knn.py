@@ -366,3 +366,31 @@ def test_knn_graph_large_sampled():
     res = judge_topk(s[pick].cpu(), i[pick].cpu(), ex_s.cpu(), ex_i.cpu(), k, SCORE_TOL)
     assert res["index_mismatch_beyond_tol"] == 0 and res["max_score_err"] <= SCORE_TOL, res
     assert not (i == torch.arange(n, device="cuda").reshape(-1, 1)).any()
+
+
+def test_concurrent_searches_on_two_streams():
+    """One store searched from two CUDA streams at once (the workspace — running lists, locks, bounds —
+    is cached per stream), k = 10 and k = 100.  Two persistent 148-CTA kernels cannot be co-resident:
+    the second one's CTA pairs start as the first one's finish, i.e. staggered by milliseconds, which
+    is exactly the situation the lockstep throttle's 2 ms give-up exists for.  Both results must
+    equal the serial ones bit for bit."""
+    n, d = 400_000, 256
+    store, g = _device_store(n, d, 21)
+    st = S.EmbeddingStore(store)
+    qa = torch.randn((6000, d), generator=g, device="cuda").to(torch.bfloat16)
+    qb = torch.randn((6000, d), generator=g, device="cuda").to(torch.bfloat16)
+    for k in (10, 100):
+        ref_a = st.search_raw(qa, k)
+        ref_b = st.search_raw(qb, k)
+        torch.cuda.synchronize()
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        outs = {}
+        for rep in range(3):
+            with torch.cuda.stream(s1):
+                outs["a"] = st.search_raw(qa, k)
+            with torch.cuda.stream(s2):
+                outs["b"] = st.search_raw(qb, k)
+        torch.cuda.synchronize()
+        assert torch.equal(outs["a"][1], ref_a[1]) and torch.equal(outs["a"][0], ref_a[0])
+        assert torch.equal(outs["b"][1], ref_b[1]) and torch.equal(outs["b"][0], ref_b[0])
+    assert len(st._workspaces) >= 3  # default stream + the two side streams
