@@ -176,8 +176,9 @@ class EmbeddingStore:
         block is added to the running lists of the previous call (same q and k)."""
         lib = _lib.load()
         nq = q.shape[0]
-        ws_bytes = max(int(lib.isx_knn_workspace_bytes(max(rows.shape[0], 1), nq, q.shape[1], k)), 256)
-        ws = self._ws(ws_bytes)
+        with torch.cuda.device(self.device):  # the size depends on the device's SM count
+            ws_bytes = max(int(lib.isx_knn_workspace_bytes(max(rows.shape[0], 1), nq, q.shape[1], k)), 256)
+            ws = self._ws(ws_bytes)
         with _lib.on_device(rows, rows_rnorm, q, q_rnorm, out_a, out_b, ws) as stream:
             rc = lib.isx_knn_search_ex(
                 rows.data_ptr(), rows_rnorm.data_ptr(), rows.shape[0], q.data_ptr(), q_rnorm.data_ptr(), nq, q.shape[1], k,
@@ -382,8 +383,9 @@ class ShardedEmbeddingStore:
         peer["step"] += 1
         stride = self.world_size * nq * k * 8  # bytes of one parity's [G][Q][k] block
         arr = (ctypes.c_void_p * self.world_size)(*[p + parity * stride for p in peer["ptrs"]])
-        ws_bytes = max(int(lib.isx_knn_workspace_bytes(max(len(st), 1), nq, st.dim, k)), 256)
-        ws = st._ws(ws_bytes)
+        with torch.cuda.device(st.device):
+            ws_bytes = max(int(lib.isx_knn_workspace_bytes(max(len(st), 1), nq, st.dim, k)), 256)
+            ws = st._ws(ws_bytes)
         sink = self.__dict__.get("_event_sink")
         with _lib.on_device(st.embeddings, q, qr, ws) as stream:
             if sink is not None:  # bench.py times the fused search + scatter kernel with CUDA events
