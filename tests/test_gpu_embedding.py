@@ -200,6 +200,7 @@ def test_embedder_preprocess_patches():
     out = EfficientNetEmbedder().cuda().preprocess_patches(dev(img), 32, stride=16)
     ref = O.preprocess_patches(img, 32, 16, layout=O.NHWC)
     assert np.array_equal(out.cpu().numpy(), ref)
+    assert T.preprocess_patches(dev(img[:0]), 32).shape == (0, 3, 32, 32)  # no images: no windows
     with pytest.raises(ValueError):
         T.preprocess_patches(dev(img), 200)
     with pytest.raises(ValueError):

@@ -345,6 +345,12 @@ def test_knn_graph_excludes_self():
         check(store, None, k, s, i, graph=True)
         assert not (i.cpu() == torch.arange(3000).reshape(-1, 1)).any()
         assert i[3, :2].tolist() == [17, 2999] and i[17, :2].tolist() == [3, 2999]
+    # fewer other rows than k: the tail is padding (-inf, -1), never the row itself
+    tiny = S.EmbeddingStore(torch.from_numpy(store[:5]).cuda())
+    ts, ti = tiny.knn_graph(10)
+    check(store[:5], None, 10, ts, ti, graph=True)
+    assert (ti[:, 4:] == -1).all() and torch.isneginf(ts[:, 4:]).all() and (ti[:, :4] >= 0).all()
+    assert S.EmbeddingStore(torch.zeros((0, 64)).cuda()).knn_graph(3)[1].shape == (0, 3)
     # a store with an index base: neighbours carry global indices and self is still excluded
     st2 = S.EmbeddingStore(torch.from_numpy(store).cuda(), index_base=500)
     s2, i2 = st2.knn_graph(5)
