@@ -7,16 +7,20 @@
 Primary line (one JSON object on stdout, rank 0):
   metric   knn_queries_per_sec — cosine k-NN, k=10, 1280-d, over a 1 M x 1280 bf16 embedding store
            with 10 k queries (BASELINE.json configs[1]).  A step = one pass of all queries over the
-           store: query inverse norms + tcgen05 GEMM with fused top-k + merge (+ one NCCL all-gather
-           and merge when the store is row-sharded over N > 1 GPUs; scaling = strong: the 1 M-row
-           store is fixed and split N ways).
-  value    device-timed (CUDA events, max over ranks), inputs resident in HBM.
+           store: query inverse norms + tcgen05 GEMM with fused top-k + merge (N > 1, store
+           row-sharded: the finalising pass stores packed records into every rank's gather buffer
+           over NVLink, barrier, merge; scaling = strong: the 1 M-row store is fixed and split N ways).
+  value    device-timed (CUDA events, max over ranks), inputs resident in HBM, after a 2 s pre-heat.
   e2e      the same metric through the public API from pinned HOST query buffers, H2D and D2H inside
            the timed region.
   roofline bf16 tensor roofline of the search kernel, timed live with CUDA events on its stream.
-  cpu_baseline  the torch-CPU port of the same workload (oracle/torch_port.py) on a bounded sample.
-  extra    stage 1 (tiles/s, HBM roofline) and stage 2 (cells/s, HBM roofline) of config 3, and at
-           N > 1 the row-sharded config-4-style search (k=100, bigger shards).
+  verify   (untimed) sampled queries through the product path against an exact fp32 brute force over
+           every rank's shard; every differing index justified by its score gap.
+  cpu_baseline  the torch-CPU port of the same workload (oracle/torch_port.py) on a bounded sample,
+           plus stage 1 / stage 2 / PCA.fit and a config-1 sample on the host cores.
+  extra    stage 1 (tiles/s, HBM roofline) and stage 2 (cells/s, HBM roofline) of config 3 on every
+           rank, PCA.fit, other search shapes, the scaled sift run; at N > 1 config 4 at its full
+           100 M-row size (k = 10 and 100, verified) and the config-5 all-pairs graph.
 
 --impl reference times the reference-side CPU implementation only (rank 0), same metric/config.
 """

@@ -5,8 +5,8 @@
 //                          fp32 accumulators in TMEM) with the per-query top-k fused into the
 //                          epilogue: the Q x N score matrix never leaves the SM.
 //   K5  topk_merge_kernel  finalises K4's running lists (scale by the queries' inverse norms, rebase
-//                          the rows) and merges the partial lists of several GPUs after the NCCL
-//                          all-gather.
+//                          the rows — as two arrays, packed records, or packed records stored into every
+//                          peer's gather buffer over NVLink) and merges the partial lists of several GPUs.
 //
 // There is no reference implementation of this stage; semantics follow
 // oracle/oracle.py::cosine_knn: normalize(q) . normalize(e) with F.normalize's eps

@@ -8,9 +8,12 @@ store holds (`storage/models.py:94-129`: float32 C×H×W BLOBs → rows of a bf1
 Single GPU:   EmbeddingStore(embeddings).search(queries, k)
 Several GPUs: ShardedEmbeddingStore — rows are split contiguously over the ranks of a
               `torch.distributed` group (one process per GPU); every rank searches its shard with the
-              fused tcgen05 kernel, one all-gather of (score, index) pairs follows, and every rank
-              merges the gathered lists.  Preprocessing and projection shard by batch and need no
-              collective.
+              fused tcgen05 kernel, whose finalising pass stores the rank's packed (score, index)
+              records into every rank's gather buffer over NVLink (peer-mapped symmetric memory; ONE
+              NCCL all-gather of the same records as the fallback); every rank merges its buffer.
+              All-pairs graphs shard the queries and rotate the store through all-gathers while the
+              running top-k lists stay in the kernel's workspace.  Preprocessing and projection
+              shard by batch and need no collective.
 """
 
 from __future__ import annotations
