@@ -161,6 +161,33 @@ def test_patch_grid_and_graph_chunk_plan():
     assert torch.equal(us, s) and torch.equal(ui, i)
 
 
+def test_similar_shape_batches_matches_reference_sampler_rule():
+    """`SimilarShapeBatcher` (data.py:403-452) on the reference test's own shape list
+    (tests/test_data.py:24-39): batches never exceed `max_batch_size`, hold one shape each, cover every
+    index once, and equal sort -> group -> chunk computed independently."""
+    import itertools
+
+    from imagescry_b200.ingest import HwcTileIngest, similar_shape_batches
+
+    shapes = [(7, 7), (7, 8), (8, 8), (8, 8), (7, 7), (5, 7), (8, 8), (8, 7), (8, 7), (7, 7), (7, 7), (2, 2), (3, 2), (2, 2)]
+    for mbs in (1, 2, 3, 4, 100):
+        got = similar_shape_batches(shapes, mbs)
+        assert all(1 <= len(b) <= mbs for b in got)
+        assert all(len({shapes[i] for i in b}) == 1 for b in got)
+        assert sorted(i for b in got for i in b) == list(range(len(shapes)))
+        want = []
+        ordered = sorted(enumerate(shapes), key=lambda t: t[1])
+        for _, grp in itertools.groupby(ordered, key=lambda t: t[1]):
+            idx = [i for i, _ in grp]
+            want += [idx[j:j + mbs] for j in range(0, len(idx), mbs)]
+        assert got == want
+    assert similar_shape_batches([], 4) == []
+    with pytest.raises(ValueError):
+        similar_shape_batches(shapes, 0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        HwcTileIngest("cpu", 4)
+
+
 def test_shard_range_partition():
     from imagescry_b200.search import shard_range
 

@@ -205,3 +205,33 @@ def test_embedder_preprocess_patches():
         T.preprocess_patches(dev(img), 200)
     with pytest.raises(ValueError):
         T.preprocess_patches(dev(img[..., :2]), 16)
+
+
+# ------------------------------------------------------------------------------------ HWC ingest (8f.3)
+def test_hwc_ingest_equals_direct_preprocess():
+    """Decoder-order tiles of mixed shapes -> pinned double-buffered staging -> NHWC kernels: every
+    same-shape batch equals `preprocess` of the reference-style NCHW stack of the same tiles (more
+    batches than staging slots, so buffers are reused)."""
+    from imagescry_b200.ingest import HwcTileIngest, preprocess_hwc_tiles, similar_shape_batches
+
+    rng = np.random.default_rng(8)
+    shapes = [(40, 48), (64, 64), (40, 48), (33, 57), (64, 64), (40, 48), (64, 64), (40, 48), (33, 57), (40, 48), (40, 48)]
+    tiles = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    tiles[3] = torch.from_numpy(tiles[3])  # torch CPU tensors are accepted as well
+    model = EfficientNetEmbedder(max_side_length=48).cuda()
+    out = preprocess_hwc_tiles(model, tiles, max_batch_size=2)
+    plan = similar_shape_batches(shapes, 2)
+    assert [i.tolist() for i, _ in out] == plan and len(plan) > 2
+    for idx, pre in out:
+        stack = np.stack([np.asarray(tiles[i]) for i in idx.tolist()])          # B H W 3, decoder order
+        nchw = torch.from_numpy(np.ascontiguousarray(stack.transpose(0, 3, 1, 2))).cuda()  # what the reference collates
+        assert torch.equal(pre, model.preprocess(nchw))
+        assert pre.device.type == "cuda" and idx.dtype == torch.int64
+    seen = []
+    for idx, batch in HwcTileIngest("cuda", 3).batches(tiles):
+        assert batch.dtype == torch.uint8 and batch.shape[1:] == (*shapes[int(idx[0])], 3)
+        assert np.array_equal(batch.cpu().numpy(), np.stack([np.asarray(tiles[i]) for i in idx.tolist()]))
+        seen += idx.tolist()
+    assert sorted(seen) == list(range(len(tiles)))
+    with pytest.raises(ValueError):
+        list(HwcTileIngest("cuda", 3).batches([np.zeros((4, 4), dtype=np.uint8)]))
