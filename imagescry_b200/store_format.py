@@ -85,7 +85,47 @@ def store_from_blobs(records: Iterable[tuple[bytes, int, int, int]], *, pool: st
     return store_from_maps(stack_blobs(records), pool=pool, index_base=index_base, device=device)
 
 
-def rows_to_image_cell(rows: Tensor | Sequence[int], cells_per_image: int) -> tuple[Tensor, Tensor]:
-    """Search result rows of a per-cell store → (image position in the stack, cell index y*W + x)."""
+def store_from_mixed_blobs(
+    records: Iterable[tuple[bytes, int, int, int]], *, pool: str | None = None, index_base: int = 0, device=None
+) -> tuple[EmbeddingStore, Tensor]:
+    """BLOB records whose maps differ in H×W (same channel count) → one search store.
+
+    A real imagescry database holds one embedding map per image and images differ in size.  The
+    reference's reader pads every map with zero cells to the largest H×W (`StoredEmbeddingsDataset`,
+    `data.py:378-399`); zero cells are not embeddings, so here nothing is padded: records are grouped by
+    shape (`SimilarShapeBatcher`'s rule), every group is converted on the GPU, and the rows of image i
+    occupy `[row_offsets[i], row_offsets[i + 1])` of the store in the records' order (one row per
+    cell in `get_flat_vectors` order, or one pooled row).  Returns `(store, row_offsets)`, `row_offsets`
+    an int64 CPU tensor of length `n + 1`; `rows_to_image_cell(rows, row_offsets)` maps hits back."""
+    from imagescry_b200.ingest import similar_shape_batches
+
+    recs = list(records)
+    if not recs:
+        raise ValueError("no embedding records")
+    dims = {r[1] for r in recs}
+    if len(dims) != 1:
+        raise ValueError(f"all embedding maps must share one channel count, got {sorted(dims)}")
+    (c,) = dims
+    per_image = [1 if pool else r[2] * r[3] for r in recs]
+    row_offsets = torch.zeros(len(recs) + 1, dtype=torch.int64)
+    row_offsets[1:] = torch.cumsum(torch.tensor(per_image, dtype=torch.int64), dim=0)
+    dev = torch.device(device or "cuda")
+    rows = torch.empty((int(row_offsets[-1]), c), dtype=torch.bfloat16, device=dev)
+    for batch in similar_shape_batches([(r[2], r[3]) for r in recs], 4096):
+        maps = stack_blobs([recs[i] for i in batch]).to(dev, non_blocking=True)
+        part = maps_to_rows(maps, pool=pool)
+        n_rows = per_image[batch[0]]
+        dst = torch.cat([torch.arange(int(row_offsets[i]), int(row_offsets[i]) + n_rows) for i in batch]).to(dev)
+        rows.index_copy_(0, dst, part)
+    return EmbeddingStore(rows, index_base=index_base), row_offsets
+
+
+def rows_to_image_cell(rows: Tensor | Sequence[int], cells_per_image: int | Tensor) -> tuple[Tensor, Tensor]:
+    """Search result rows of a per-cell store → (image position in the stack, cell index y*W + x).
+    `cells_per_image`: the common cell count, or the `row_offsets` of `store_from_mixed_blobs`."""
     r = torch.as_tensor(rows)
+    if isinstance(cells_per_image, Tensor):
+        offsets = cells_per_image.to(r.device)
+        img = torch.searchsorted(offsets, r, right=True) - 1
+        return img, r - offsets[img]
     return torch.div(r, cells_per_image, rounding_mode="floor"), r % cells_per_image

@@ -400,3 +400,30 @@ def test_concurrent_searches_on_two_streams():
         assert torch.equal(outs["a"][1], ref_a[1]) and torch.equal(outs["a"][0], ref_a[0])
         assert torch.equal(outs["b"][1], ref_b[1]) and torch.equal(outs["b"][0], ref_b[0])
     assert len(st._workspaces) >= 3  # default stream + the two side streams
+
+
+def test_store_from_mixed_shape_blobs():
+    """A database whose maps differ in H×W (what the reference's reader zero-pads, data.py:378-399):
+    nothing is padded, image i's cells are rows [offsets[i], offsets[i + 1]) and equal the oracle's
+    rows of that map bit for bit; a query built from one cell finds that (image, cell)."""
+    from imagescry_b200 import store_format as F
+
+    rng = np.random.default_rng(13)
+    shapes = [(3, 4), (5, 6), (3, 4), (2, 7), (5, 6), (3, 4)]
+    maps = [rng.standard_normal((72, h, w)).astype(np.float32) for h, w in shapes]
+    records = [(O.blob_encode(m), 72, m.shape[1], m.shape[2]) for m in maps]
+    store, offsets = F.store_from_mixed_blobs(records)
+    assert offsets.tolist() == [0, 12, 42, 54, 68, 98, 110] and len(store) == 110
+    rows = store.embeddings.float().cpu().numpy()
+    for i, m in enumerate(maps):
+        assert np.array_equal(rows[int(offsets[i]):int(offsets[i + 1])], O.maps_to_rows(m[None]))
+    q = torch.from_numpy(maps[3][:, 1, 5]).reshape(1, -1).cuda()
+    s, idx = store.search(q, 2)
+    img, cell = F.rows_to_image_cell(idx[0, :1].cpu(), offsets)
+    assert (int(img), int(cell)) == (3, 1 * 7 + 5)
+    pooled, poff = F.store_from_mixed_blobs(records, pool="mean")
+    assert poff.tolist() == list(range(7)) and len(pooled) == 6
+    ref = np.stack([O.maps_to_rows(m[None], pool="mean")[0] for m in maps])
+    assert np.abs(pooled.embeddings.float().cpu().numpy() - ref).max() <= np.abs(ref).max() * 2.0**-7
+    with pytest.raises(ValueError):
+        F.store_from_mixed_blobs(records + [(O.blob_encode(maps[0][:8]), 8, 3, 4)])
