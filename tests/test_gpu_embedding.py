@@ -235,3 +235,65 @@ def test_hwc_ingest_equals_direct_preprocess():
     assert sorted(seen) == list(range(len(tiles)))
     with pytest.raises(ValueError):
         list(HwcTileIngest("cuda", 3).batches([np.zeros((4, 4), dtype=np.uint8)]))
+
+
+# ------------------------------------------------------------------------------------ end-to-end sift
+def test_sift_end_to_end_small(golden):
+    """Config 5 in miniature on one GPU: HWC tiles -> preprocess -> (tiny conv backbone, torch, not owned)
+    -> L2 + mean pool + PCA -> all-pairs graph, against the oracle's composition of the same stages."""
+    from imagescry_b200.image.transforms import preprocess_tiles
+    from imagescry_b200.models.decomposition import PCA
+    from imagescry_b200.models.embedding import EmbeddingModule
+    from imagescry_b200.sift import sift
+
+    g = golden("embed_pca")
+
+    class Tiny(EmbeddingModule):
+        def __init__(self):
+            super().__init__()
+            self.net = torch.nn.Sequential(torch.nn.Conv2d(3, 64, 8, stride=8), torch.nn.SiLU())
+
+        def preprocess(self, images):
+            return preprocess_tiles(images, min_value=-3, max_value=3)
+
+        def preprocess_hwc(self, tiles):
+            return preprocess_tiles(tiles, layout="nhwc", min_value=-3, max_value=3)
+
+        def forward(self, x):
+            return self.net(x)
+
+        @property
+        def embedding_dim(self):
+            return 64
+
+    model = Tiny()
+    model.net[0].weight.data = torch.from_numpy(g["pipe_conv_w"])
+    model.net[0].bias.data = torch.from_numpy(g["pipe_conv_b"])
+    model = model.cuda().eval()
+    rng = np.random.default_rng(2)
+    tiles = rng.integers(0, 256, (300, 32, 48, 3), dtype=np.uint8)
+    comps = np.linalg.qr(rng.standard_normal((64, 16)))[0].astype(np.float32)
+    means = (rng.standard_normal(64) * 0.01).astype(np.float32)
+    pca = PCA(num_features=64, num_components=16)
+    pca.feature_means.data = torch.from_numpy(means).reshape(1, -1)
+    pca.component_vectors.data = torch.from_numpy(comps)
+    pca._fitted.data = torch.tensor(True)
+    pca._num_features.data = torch.tensor(64)
+    pca._num_components.data = torch.tensor(16)
+    pca = pca.cuda()
+    rows, scores, idx = sift(model, pca, dev(tiles), 5, batch_size=128)
+    assert rows.shape == (300, 16) and idx.shape == (300, 5)
+    # oracle composition, batch by batch (batch statistics per batch)
+    ref_rows = []
+    for s in range(0, 300, 128):
+        pre = O.preprocess(tiles[s:s + 128], layout=O.NHWC)
+        with torch.inference_mode():
+            fmap = model(torch.from_numpy(pre).cuda()).cpu().numpy()
+        ref_rows.append(O.pipeline_project(fmap, means, comps, pool="mean"))
+    ref_rows = np.concatenate(ref_rows)
+    assert np.abs(rows.cpu().numpy() - ref_rows).max() <= 1e-4 * np.abs(ref_rows).max()
+    # the graph of the rows the product produced (bf16 store of those rows) against the oracle's graph
+    from test_gpu_knn import check
+
+    store_rows = O.bf16_round(rows.cpu().numpy())
+    check(store_rows, None, 5, scores, idx, graph=True)
