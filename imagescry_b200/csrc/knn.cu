@@ -344,6 +344,60 @@ __device__ __forceinline__ void prune_row(uint2* row_buf, int swz, int count, in
   }
 }
 
+// In-tile prune of a LARGE buffer (k > 16: 256 entries in global memory) without sorting it: the k-th
+// best score is found by a bitwise bisection over the order-preserving integer image of the scores
+// (32 rounds of warp ballots over the lanes' registers), and the entries at or above it are compacted
+// to the front of the buffer, unsorted — order only matters at the item end, which sorts what is left.
+// About 1100 instructions against about 2600 for the 256-entry bitonic network plus its stores.
+// Ties at the k-th score are all kept (they arrived earlier, i.e. they have lower rows than anything
+// that can still arrive in this item); if so many tie that the buffer would stay more than half-way
+// to full, the caller falls back to the sorting prune, which keeps exactly k.  Returns false then.
+template <int CAP>
+__device__ __forceinline__ bool prune_row_select(uint2* row_buf, int count, int k, float& new_thr, int& new_count) {
+  constexpr int E = CAP / 32;
+  const int lane = static_cast<int>(lane_id());
+  uint2 v[E];
+  uint32_t enc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    v[e] = make_uint2(0u, 0u);
+    enc[e] = 0u;  // below every real score
+    if (i < count) {
+      v[e] = row_buf[i];
+      enc[e] = thr_encode(__uint_as_float(v[e].x));
+    }
+  }
+  __syncwarp();
+  uint32_t prefix = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = prefix | (1u << bit);
+    int ge = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) ge += __popc(__ballot_sync(kFullMask, enc[e] >= cand));
+    if (ge >= k) prefix = cand;
+  }
+  // prefix = the k-th largest encoded score
+  int kept_total = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) kept_total += __popc(__ballot_sync(kFullMask, enc[e] >= prefix));
+  if (2 * kept_total > CAP + k) return false;  // a pile of ties: let the sorting prune cut to exactly k
+  int kept = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool kp = enc[e] >= prefix;
+    const uint32_t bal = __ballot_sync(kFullMask, kp);
+    if (kp) row_buf[kept + __popc(bal & ((1u << lane) - 1u))] = v[e];
+    kept += __popc(bal);
+  }
+  __syncwarp();
+  new_count = kept;
+  // decode: prefix is the encoding of the k-th best score itself
+  new_thr = __uint_as_float((prefix & 0x80000000u) ? (prefix & 0x7FFFFFFFu) : ~prefix);
+  return true;
+}
+
 template <int CAP, int NCTA, bool RES>
 __global__ void __launch_bounds__(knn_threads(CAP), 1)
 knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
@@ -628,8 +682,15 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const int c = __shfl_sync(kFullMask, cnt, rr);
             float nthr;
             int ncnt;
-            prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr, ncnt,
-                           s_reg, i_reg);
+            bool done = false;
+            if constexpr (!L::kSmemCand) {
+              // large buffers: select the k-th best and compact, no sort (c >= k here: a prune is only
+              // asked for when the buffer is close to full)
+              if (c >= p.k) done = prune_row_select<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, c, p.k, nthr, ncnt);
+            }
+            if (!done)
+              prune_row<CAP>(warp_buf + static_cast<size_t>(rr) * cand_stride, L::kSmemCand ? rr : 0, c, p.k, nthr, ncnt,
+                             s_reg, i_reg);
             __syncwarp();
             if (lane == rr) {
               cnt = ncnt;
