@@ -670,7 +670,11 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // when the appends of this chunk could overflow it.  Rows whose threshold is still so low that
         // more groups survive than a pruned buffer can take (cold start) use the windowed walk.
         // Measured and dropped: (a) a cheaper chunk-level bound (raw maximum times the chunk's largest
-        // inverse norm): at a 1-in-10^5 selection rate a bound 5 % loose passes 3-5 x as often;
+        // inverse norm): at a 1-in-10^5 selection rate a bound 5 % loose passes 3-5 x as often; with the
+        // store SORTED by norm (row ids carried beside it) the bound is tight and only 0.66 of a warp's 4
+        // chunks per tile reach the scaling, but the fast path is not bound by those instructions
+        // (2690 -> 2530 select cycles per tile at d = 256) while the id lookup in the appends and the
+        // tie handling a permuted order needs double the cost of a rare-path event: 6.2 ms against 4.4;
         // (b) a warp-cooperative walk, one surviving row at a time (ballot + popc ranking): rows with
         // survivors come in groups, and serialising them costs more than a predicated walk.
         auto prune_rows = [&](uint32_t need) {
@@ -1088,7 +1092,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
     if (warp == kEpilogueWarp0 && lane == 0 && rank == 0) {
       ISX_PROF_FLUSH(4); ISX_PROF_FLUSH(5); ISX_PROF_FLUSH(6); ISX_PROF_FLUSH(8);
-      ISX_PROF_FLUSH(9); ISX_PROF_FLUSH(10); ISX_PROF_FLUSH(12); ISX_PROF_FLUSH(13); ISX_PROF_FLUSH(14); ISX_PROF_FLUSH(15);
+      ISX_PROF_FLUSH(9); ISX_PROF_FLUSH(10); ISX_PROF_FLUSH(11); ISX_PROF_FLUSH(12); ISX_PROF_FLUSH(13); ISX_PROF_FLUSH(14); ISX_PROF_FLUSH(15);
     }
 #ifdef ISX_KNN_PROFILE
     if (warp == kEpilogueWarp0 && rank == 0) {  // appends: summed over the warp's 32 rows

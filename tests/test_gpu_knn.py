@@ -96,8 +96,8 @@ def test_knn_vs_oracle(n, q, d, k):
 
 @pytest.mark.parametrize("n,q,d,k", [(20000, 300, 256, 10), (9000, 140, 128, 100)])
 def test_knn_heterogeneous_norms(n, q, d, k):
-    """Store rows whose norms span four decades: the epilogue's chunk-level bound (raw maximum times
-    the chunk's largest inverse norm) is then loose, and the exact per-column scaling must decide."""
+    """Store rows whose norms span four decades: raw dot products say nothing about the ranking, the
+    per-column scaling by the inverse norms decides."""
     rng = np.random.default_rng(n + k)
     store, queries = make(n, q, d, seed=n * 3 + k)
     store = O.bf16_round(store * (10.0 ** rng.uniform(-2, 2, size=(n, 1))).astype(np.float32))
@@ -106,6 +106,31 @@ def test_knn_heterogeneous_norms(n, q, d, k):
     st = S.EmbeddingStore(torch.from_numpy(store).cuda())
     scores, idx = st.search(torch.from_numpy(queries).cuda(), k)
     check(store, queries, k, scores, idx)
+
+
+@pytest.mark.parametrize("k", [1, 10, 16, 40, 100])
+def test_knn_exact_ties_across_norms(k):
+    """Rows that are power-of-two multiples of one another have bit-identical cosine scores but
+    different norms; every query's best hits are a dozen such copies spread over the store (other
+    splits, other tiles, other CTAs), and each tie must go to the lower index.  Indices must match
+    the oracle exactly."""
+    rng = np.random.default_rng(77 + k)
+    n, q, d, base = 6000, 200, 64, 500
+    proto = O.bf16_round(rng.standard_normal((base, d)).astype(np.float32))
+    src = rng.integers(0, base, size=n)
+    scale = (2.0 ** rng.integers(-3, 4, size=(n, 1))).astype(np.float32)
+    store = O.bf16_round(proto[src] * scale)          # exact: powers of two
+    queries = O.bf16_round(proto[rng.integers(0, base, size=q)] + 0.25 * rng.standard_normal((q, d)).astype(np.float32))
+    st = S.EmbeddingStore(torch.from_numpy(store).cuda())
+    scores, idx = st.search(torch.from_numpy(queries).cuda(), k)
+    ref_s, ref_i = O.cosine_knn(store, queries, k)
+    assert np.array_equal(idx.cpu().numpy(), ref_i)
+    assert np.abs(scores.cpu().numpy() - ref_s).max() <= SCORE_TOL
+    # every query's best hits are one prototype's copies: ties by the dozen (n / base = 12 copies each)
+    assert (ref_s[:, 0] == ref_s[:, min(k, 3) - 1]).mean() > 0.9
+    gs, gi = st.knn_graph(min(k, 16))
+    gref_s, gref_i = O.knn_graph(store, min(k, 16))
+    assert np.array_equal(gi.cpu().numpy(), gref_i)
 
 
 @pytest.mark.parametrize("n,q,k", [(150, 40, 128), (200, 300, 128), (20, 5, 16), (300, 50, 128), (520, 257, 128), (700, 64, 100)])
