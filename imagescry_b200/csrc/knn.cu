@@ -53,7 +53,11 @@ constexpr int kEpilogueWarp0 = 4;
 // TMEM / shared-memory latencies (d = 256: the epilogue, not the MMA, was the limiter with one group).
 // Large k (256-entry candidate buffers in global memory, long sorts) keeps one group: there the
 // second set of per-row lists costs more than the shorter fast path saves.
+#ifdef ISX_KNN_ONE_GROUP  // diagnostic A/B only (with the pipelined loads: d = 256 4.83 ms against 4.38, d = 64 4.57 against 3.64)
+__host__ __device__ constexpr int epi_groups(int) { return 1; }
+#else
 __host__ __device__ constexpr int epi_groups(int cap) { return cap <= 32 ? 2 : 1; }
+#endif
 __host__ __device__ constexpr int knn_threads(int cap) { return kEpilogueWarp0 * 32 + 128 * epi_groups(cap); }
 constexpr int kMaxK = 128;
 constexpr int kSmallK = 16;  // k <= kSmallK keeps candidate buffers in shared memory
@@ -215,10 +219,12 @@ struct KnnParams {
 // Diagnostic build (-DISX_KNN_PROFILE): every role accumulates the cycles it spends in each wait and
 // adds them to p.prof at the end; the host prints them per CTA.  Compiled out otherwise.
 #ifdef ISX_KNN_PROFILE
-#define ISX_PROF_DECL unsigned long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t0 = 0, prof_t1 = 0; (void)prof_t0; (void)prof_t1
+#define ISX_PROF_DECL unsigned long long prof_acc[24] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t0 = 0, prof_t1 = 0, prof_t2 = 0; (void)prof_t0; (void)prof_t1; (void)prof_t2
 #define ISX_PROF_COUNT(slot, v) prof_acc[slot] += (v)
 #define ISX_PROF_BEGIN1() prof_t1 = clock64()
 #define ISX_PROF_END1(slot) prof_acc[slot] += static_cast<unsigned long long>(clock64() - prof_t1)
+#define ISX_PROF_BEGIN2() prof_t2 = clock64()
+#define ISX_PROF_END2(slot) prof_acc[slot] += static_cast<unsigned long long>(clock64() - prof_t2)
 #define ISX_PROF_BEGIN() prof_t0 = clock64()
 #define ISX_PROF_END(slot) prof_acc[slot] += static_cast<unsigned long long>(clock64() - prof_t0)
 #define ISX_PROF_FLUSH(slot) atomicAdd(p.prof + (slot), prof_acc[slot])
@@ -227,6 +233,8 @@ struct KnnParams {
 #define ISX_PROF_COUNT(slot, v)
 #define ISX_PROF_BEGIN1()
 #define ISX_PROF_END1(slot)
+#define ISX_PROF_BEGIN2()
+#define ISX_PROF_END2(slot)
 #define ISX_PROF_BEGIN()
 #define ISX_PROF_END(slot)
 #define ISX_PROF_FLUSH(slot)
@@ -678,6 +686,9 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // (b) a warp-cooperative walk, one surviving row at a time (ballot + popc ranking): rows with
         // survivors come in groups, and serialising them costs more than a predicated walk.
         auto prune_rows = [&](uint32_t need) {
+          if (need) ISX_PROF_BEGIN2();
+          const uint32_t need0 = need;
+          (void)need0;
           while (need) {
             ISX_PROF_COUNT(12, 1);
             const int rr = __ffs(need) - 1;
@@ -704,6 +715,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               }
             }
           }
+          if (need0) { ISX_PROF_END2(16); ISX_PROF_COUNT(17, 1); }
         };
         // scale one chunk by the inverse norms; maxima of its eight 4-column groups and of the chunk
         auto scale_chunk = [&](uint32_t (&r)[32], int cbase, float (&g)[8]) -> float {
@@ -733,9 +745,29 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           int ngrp = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) ngrp += (g[j] > thr) ? 1 : 0;
+          ISX_PROF_COUNT(20, __popc(__ballot_sync(kFullMask, hit)));
           if (CAP - kSmallK >= 32 || !__any_sync(kFullMask, hit && 4 * ngrp > CAP - p.k)) {
             prune_rows(__ballot_sync(kFullMask, hit && cnt + 4 * ngrp > CAP));
-            if (hit) {
+            ISX_PROF_BEGIN2();
+            // chunks that hold neither the end of the store nor a row's own column (all but a handful)
+            // append branch-free: one compare and a handful of predicated instructions per column, no
+            // dependent chain but the counter.  The walk group by group with its per-group branches
+            // costs a single warp ~980 cycles per event (latency of a serial, divergent instruction
+            // stream), this one ~750 (-DISX_KNN_PROFILE; k = 100 at d = 256: 10.9 -> 9.9 ms).
+            const bool edge = cbase + 32 > ncols || static_cast<uint32_t>(self_row - gcol0 - cbase) < 32u;
+            if (!__any_sync(kFullMask, hit && edge)) {
+              if (hit) {
+                ISX_PROF_COUNT(11, static_cast<unsigned long long>(-cnt));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const bool take = __uint_as_float(r[j]) > thr;
+                  if (take) my_buf[cnt ^ my_swz] = make_uint2(r[j], static_cast<uint32_t>(gcol0 + cbase + j));
+                  cnt += take ? 1 : 0;
+                }
+                ISX_PROF_COUNT(11, static_cast<unsigned long long>(cnt));
+                row_best = fmaxf(row_best, vmax);  // the chunk's maximum is one of the appended scores
+              }
+            } else if (hit) {
 #pragma unroll
               for (int gi = 0; gi < 8; ++gi) {
                 if (g[gi] > thr) {
@@ -752,7 +784,10 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 }
               }
             }
+            __syncwarp();
+            ISX_PROF_END2(21);
           } else {
+            ISX_PROF_COUNT(19, 1);
 #pragma unroll
             for (int h = 0; h < 32 / CHUNK; ++h) {
               prune_rows(__ballot_sync(kFullMask, cnt > CAP - CHUNK));
@@ -779,11 +814,8 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         ISX_PROF_BEGIN();
         const int c0 = eg * kGroupCols;  // this group's first column of the tile
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c0;
-        // Two chunks (64 columns) per step: both TMEM loads are issued together and their scaling and
-        // max trees are independent instruction streams, so a warp rarely stalls on its own
-        // dependencies; one warp-uniform test covers both chunks.
-        // (Loading a group's whole 128-column share first and releasing the stage before any selection
-        // was measured too: slower, d = 256 5.8 ms against 4.6 — the epilogue is bound by its own
+        // (Measured and dropped: loading a group's whole 128-column share first and releasing the stage
+        // before any selection: slower, d = 256 5.8 ms against 4.6 — the epilogue is bound by its own
         // instruction stream, ~180 scheduler cycles per 32 columns of which the inverse-norm loads and
         // multiplies are 64, not by the hand-off.  A bound per 4-column group — raw group maximum times
         // the group's largest inverse norm, 30 instructions per chunk in front of the exact scaling —
@@ -792,13 +824,31 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // the staging barrier: 10.2 ms against 4.4 at d = 256 — the L1 path cannot feed 8 broadcast
         // 16-byte loads per 32 columns and warp.)
         uint32_t ra[32], rb[32];
+        // Software pipeline over the 32-column chunks with two register buffers: the tcgen05.ld of chunk
+        // c + 1 is in flight while chunk c is scaled and tested, so a warp's load latency (~300 cycles
+        // while the pair's MMAs run) hides behind its own instruction stream instead of relying on the
+        // other warp of its scheduler.  Against issuing both loads of a 64-column step together and
+        // waiting for both: d = 256 4.51 -> 4.38 ms, d = 64 3.91 -> 3.65 ms, the 500 k x 256 graph
+        // 124.9 -> 118.5 ms, 164 -> 148 registers (same box, back to back).
+        tmem_ld_32x32(taddr, ra);
 #pragma unroll 1
         for (int ld = 0; ld < kGroupCols / 32; ld += 2) {
-          tmem_ld_32x32(taddr + ld * 32, ra);
-          tmem_ld_32x32(taddr + (ld + 1) * 32, rb);
+          const int cb = c0 + ld * 32;
           tc_wait_ld_regs(ra);
+          tmem_ld_32x32(taddr + (ld + 1) * 32, rb);
+          ISX_PROF_COUNT(9, 2);
+#ifdef ISX_KNN_PROFILE
+          if (!(p.debug_skip_select & 1))
+#endif
+          {
+            float ga[8];
+            const float va = scale_chunk(ra, cb, ga);
+            collect_chunk(ra, cb, ga, va);
+          }
           tc_wait_ld_regs(rb);
-          if (ld + 2 >= kGroupCols / 32) {
+          if (ld + 2 < kGroupCols / 32) {
+            tmem_ld_32x32(taddr + (ld + 2) * 32, ra);
+          } else {
             // every TMEM read of this tile has landed: release the accumulator stage
             tc_fence_before();
             __syncwarp();
@@ -807,15 +857,11 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
           }
 #ifdef ISX_KNN_PROFILE
-          if (p.debug_skip_select & 1) continue;
+          if (!(p.debug_skip_select & 1))
 #endif
-          float ga[8], gb[8];
-          const int cb = c0 + ld * 32;
-          const float va = scale_chunk(ra, cb, ga);
-          const float vb = scale_chunk(rb, cb + 32, gb);
-          ISX_PROF_COUNT(9, 2);
-          if (__any_sync(kFullMask, fmaxf(va, vb) > thr)) {
-            collect_chunk(ra, cb, ga, va);
+          {
+            float gb[8];
+            const float vb = scale_chunk(rb, cb + 32, gb);
             collect_chunk(rb, cb + 32, gb, vb);
           }
         }
@@ -944,7 +990,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
           ISX_PROF_COUNT(15, 1);
         }
-        ISX_PROF_END1(13);
+        ISX_PROF_END1(18);
       } else {
         // 256-entry buffers (k > 16), the same phase structure: the per-row chain used to be
         // sort -> lock spin -> fence -> running-list loads -> merge -> stores -> fence -> unlock, ~18 k cycles
@@ -1092,7 +1138,7 @@ knn_search_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
     if (warp == kEpilogueWarp0 && lane == 0 && rank == 0) {
       ISX_PROF_FLUSH(4); ISX_PROF_FLUSH(5); ISX_PROF_FLUSH(6); ISX_PROF_FLUSH(8);
-      ISX_PROF_FLUSH(9); ISX_PROF_FLUSH(10); ISX_PROF_FLUSH(11); ISX_PROF_FLUSH(12); ISX_PROF_FLUSH(13); ISX_PROF_FLUSH(14); ISX_PROF_FLUSH(15);
+      ISX_PROF_FLUSH(9); ISX_PROF_FLUSH(10); ISX_PROF_FLUSH(11); ISX_PROF_FLUSH(12); ISX_PROF_FLUSH(16); ISX_PROF_FLUSH(17); ISX_PROF_FLUSH(18); ISX_PROF_FLUSH(19); ISX_PROF_FLUSH(20); ISX_PROF_FLUSH(21); ISX_PROF_FLUSH(22); ISX_PROF_FLUSH(13); ISX_PROF_FLUSH(14); ISX_PROF_FLUSH(15);
     }
 #ifdef ISX_KNN_PROFILE
     if (warp == kEpilogueWarp0 && rank == 0) {  // appends: summed over the warp's 32 rows
@@ -1402,8 +1448,8 @@ static int knn_search_impl(const char* fn, const void* store, const float* store
 
 #ifdef ISX_KNN_PROFILE
   static unsigned long long* d_prof = nullptr;
-  if (!d_prof) ISX_CHECK_CUDA(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
-  ISX_CHECK_CUDA(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream));
+  if (!d_prof) ISX_CHECK_CUDA(cudaMalloc(&d_prof, 24 * sizeof(unsigned long long)));
+  ISX_CHECK_CUDA(cudaMemsetAsync(d_prof, 0, 24 * sizeof(unsigned long long), stream));
   p.prof = d_prof;
   p.debug_skip_select = getenv("ISX_KNN_SKIP_SELECT") ? atoi(getenv("ISX_KNN_SKIP_SELECT")) : 0;
 #endif
@@ -1420,7 +1466,7 @@ static int knn_search_impl(const char* fn, const void* store, const float* store
   if (rc != ISX_OK) return rc;
 #ifdef ISX_KNN_PROFILE
   {
-    unsigned long long h[16];
+    unsigned long long h[24];
     ISX_CHECK_CUDA(cudaStreamSynchronize(stream));
     ISX_CHECK_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
     const double units = static_cast<double>(plan.grid / ncta);
@@ -1434,8 +1480,9 @@ static int knn_search_impl(const char* fn, const void* store, const float* store
             h[8] / units / tiles);
     fprintf(stderr,
             "isx knn profile (warp 4 of every leader CTA, per tile): chunks %.2f, with survivors %.3f, appends %.3f, "
-            "prunes %.3f, cycles in the rare path + item-end lock/merge phases %.0f; per item: rows merged %.1f, lock rounds %.1f\n",
-            h[9] / units / tiles, h[10] / units / tiles, h[11] / units / tiles, h[12] / units / tiles, h[13] / units / tiles,
+            "prunes %.3f (in %.3f calls, %.0f cycles), cycles in the rare path %.0f (group walks %.0f; windowed events %.4f; rows with survivors %.3f), in the item-end lock/merge phases %.0f; per item: rows merged %.1f, lock rounds %.1f\n",
+            h[9] / units / tiles, h[10] / units / tiles, h[11] / units / tiles, h[12] / units / tiles, h[17] / units / tiles,
+            h[16] / units / tiles, h[13] / units / tiles, h[21] / units / tiles, h[19] / units / tiles, h[20] / units / tiles, h[18] / units / tiles,
             h[14] / units / (static_cast<double>(plan.items) / units), h[15] / units / (static_cast<double>(plan.items) / units));
   }
 #endif
