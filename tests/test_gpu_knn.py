@@ -454,3 +454,29 @@ def test_store_from_mixed_shape_blobs():
     assert np.abs(pooled.embeddings.float().cpu().numpy() - ref).max() <= np.abs(ref).max() * 2.0**-7
     with pytest.raises(ValueError):
         F.store_from_mixed_blobs(records + [(O.blob_encode(maps[0][:8]), 8, 3, 4)])
+
+
+def test_search_host_batches_streams_ragged_batches():
+    """Streamed search from pinned host batches (copy stream around the search) returns, batch by
+    batch, what the direct search returns; ragged and unpinned batches, and an early exit."""
+    store, queries = make(20000, 1000, 128, seed=5)
+    st = S.EmbeddingStore(torch.from_numpy(store).cuda())
+    cuts = [0, 300, 600, 617, 617 + 256, 1000]
+    host = [torch.from_numpy(queries[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    host = [h.pin_memory() if j % 2 == 0 else h for j, h in enumerate(host)]
+    want_s, want_i = st.search_raw(torch.from_numpy(queries).cuda(), 10)
+    got = []
+    for s_h, i_h in S.search_host_batches(st, host, 10):
+        assert s_h.device.type == "cpu" and s_h.is_pinned() and i_h.dtype == torch.int32
+        got.append((s_h.clone(), i_h.clone()))
+    assert [g[0].shape[0] for g in got] == [b - a for a, b in zip(cuts[:-1], cuts[1:])]
+    assert torch.equal(torch.cat([g[1] for g in got]), want_i.cpu())
+    assert torch.equal(torch.cat([g[0] for g in got]), want_s.cpu())
+    assert list(S.search_host_batches(st, [], 10)) == []
+    gen = S.search_host_batches(st, host, 10)
+    first = next(gen)
+    assert torch.equal(first[1], want_i[:300].cpu())
+    gen.close()  # abandoning the stream mid-way must leave nothing in flight
+    with pytest.raises(ValueError):
+        list(S.search_host_batches(st, [torch.zeros(5)], 10))
+    check(store, queries[:300], 10, got[0][0], got[0][1].to(torch.int64))

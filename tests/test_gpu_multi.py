@@ -57,6 +57,13 @@ for k in (10, 100):
         assert torch.equal(i1, i2) and torch.equal(s1, s2), (rank, k, rep)
 assert nccl_sharded.gather_path == "nccl"
 del os.environ["ISX_PEER_GATHER"]
+# streamed host batches (H2D / D2H on a copy stream around the sharded search) == the direct search
+from imagescry_b200.search import search_host_batches
+host_batches = [torch.from_numpy(queries[:128]).pin_memory(), torch.from_numpy(queries[128:131]).pin_memory(),
+                torch.from_numpy(queries[131:]).pin_memory()]
+got = [(s.clone(), i.clone()) for s, i in search_host_batches(sharded, host_batches, 10)]
+ws, wi = sharded.search_raw(qd, 10)
+assert torch.equal(torch.cat([g[1] for g in got]), wi.cpu()) and torch.equal(torch.cat([g[0] for g in got]), ws.cpu()), rank
 # all-pairs graph over the sharded store (config 5): queries sharded, store rotated through the
 # all-gather, running lists kept in the kernel workspace == the single-GPU graph == the oracle
 gn = 5003
