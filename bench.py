@@ -12,7 +12,7 @@ Primary line (one JSON object on stdout, rank 0):
            over NVLink, barrier, merge; scaling = strong: the 1 M-row store is fixed and split N ways).
   value    device-timed (CUDA events, max over ranks), inputs resident in HBM, after a 2 s pre-heat.
   e2e      the same metric through the public API from pinned HOST query buffers, every step's H2D
-           and D2H inside the timed region: `value` streams the steps through search_host_batches
+           and D2H inside the timed region: `value` streams the steps through HostBatchSearch.run
            (copies on a copy stream beside the neighbouring step's search), `one_batch_at_a_time` is
            the strictly sequential form (upload, search, download, host sync).
   roofline bf16 tensor roofline of the search kernel, timed live with CUDA events on its stream.
@@ -873,13 +873,15 @@ def run_b200(args) -> None:
     # of step i + 1 and the D2H of step i ride a copy stream (DMA engines) beside the search of the
     # neighbouring step.  Every step still uploads its queries from pinned host memory and downloads
     # its result inside the timed region; every rank uploads the whole batch over its own PCIe link.
-    from imagescry_b200.search import search_host_batches
+    from imagescry_b200.search import HostBatchSearch
+
+    streamer = HostBatchSearch(sharded if dist_on else store, K)
 
     def e2e_stream(nsteps: int):
         if dist_on:
             sharded._event_sink = None
         got = 0
-        for s_h, _ in search_host_batches(sharded if dist_on else store, (q_host for _ in range(nsteps)), K):
+        for s_h, _ in streamer.run(q_host for _ in range(nsteps)):
             got += s_h.shape[0]
         assert got == nsteps * Q
 
@@ -904,7 +906,7 @@ def run_b200(args) -> None:
     e2e = {
         "value": Q / sec_stream, "unit": UNIT, "h2d_bytes_per_step": q_host.numel() * 2,
         "d2h_bytes_per_step": out_s_host.numel() * 4 + out_i_host.numel() * 4, "ms_per_step": sec_stream * 1e3,
-        "api": ("search_host_batches(store, host_batches, k): pinned host query batches streamed through "
+        "api": ("HostBatchSearch(store, k).run(host_batches): pinned host query batches streamed through "
                 + ("ShardedEmbeddingStore.search_raw (every rank uploads the batch over its own PCIe link; gather of packed "
                    f"records: {sharded.gather_path})" if dist_on else "EmbeddingStore.search_raw")
                 + "; H2D of step i+1 and D2H of step i on a copy stream beside the search; bytes are per rank"),

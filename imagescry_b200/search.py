@@ -506,95 +506,106 @@ class ShardedEmbeddingStore:
         return staging[:q]
 
 
-def search_host_batches(store, host_batches, k: int):
+class HostBatchSearch:
     """Streamed search of query batches that live in (pinned) HOST memory, for serving loops.
 
-    Yields `(scores, indices)` per batch as PINNED HOST tensors (fp32 Q×k, int32 Q×k global rows), in
-    order.  The host→device copy of batch i + 1 and the device→host copy of batch i run on a copy
-    stream (DMA engines, no SMs) while the neighbouring batch is searched on the caller's current
-    stream, so the PCIe transfers cost no search time; with a row-sharded store every rank passes
-    the same batches (each uploads them over its own PCIe link).  A yielded pair stays valid until
-    the generator is advanced again.  `store` is an `EmbeddingStore` or a `ShardedEmbeddingStore`.
-    """
-    local = store.local if isinstance(store, ShardedEmbeddingStore) else store
-    dev = local.device
-    if dev.type != "cuda":
-        raise RuntimeError(f"search_host_batches needs a CUDA store (got {dev}); there is no CPU path")
-    local._check_k(k)
-    compute = torch.cuda.current_stream(dev)
-    copy = torch.cuda.Stream(dev)
-    q_dev: list[Tensor | None] = [None, None]
-    q_n = [0, 0]
-    out_s: list[Tensor | None] = [None, None]
-    out_i: list[Tensor | None] = [None, None]
-    r_n = [0, 0]
-    uploaded: list[torch.cuda.Event | None] = [None, None]    # H2D of the slot's queries finished
-    searched: list[torch.cuda.Event | None] = [None, None]    # the search that read the slot finished
-    downloaded: list[torch.cuda.Event | None] = [None, None]  # D2H of the slot's result finished
-    keep: list[tuple | None] = [None, None]                    # device results until their D2H is done
+    `run(host_batches)` yields `(scores, indices)` per batch as PINNED HOST tensors (fp32 Q×k, int32
+    Q×k global rows), in order.  The host→device copy of batch i + 1 and the device→host copy of
+    batch i run on a copy stream (DMA engines, no SMs) while the neighbouring batch is searched on the
+    caller's current stream, so the PCIe transfers cost no search time; with a row-sharded store every
+    rank passes the same batches (each uploads them over its own PCIe link).  A yielded pair stays
+    valid until the generator is advanced again.  The staging buffers (two device query buffers, two
+    pinned result pairs) and the copy stream live as long as the object: keep it across calls.
+    `store` is an `EmbeddingStore` or a `ShardedEmbeddingStore`."""
 
-    def upload(slot: int, hb: Tensor) -> None:
+    def __init__(self, store, k: int) -> None:
+        self.store = store
+        local = store.local if isinstance(store, ShardedEmbeddingStore) else store
+        self.device = local.device
+        if self.device.type != "cuda":
+            raise RuntimeError(f"HostBatchSearch needs a CUDA store (got {self.device}); there is no CPU path")
+        local._check_k(k)
+        self.k = k
+        self._copy = torch.cuda.Stream(self.device)
+        self._q_dev: list[Tensor | None] = [None, None]
+        self._q_n = [0, 0]
+        self._out_s: list[Tensor | None] = [None, None]
+        self._out_i: list[Tensor | None] = [None, None]
+        self._r_n = [0, 0]
+        self._uploaded: list[torch.cuda.Event | None] = [None, None]    # H2D of the slot's queries finished
+        self._searched: list[torch.cuda.Event | None] = [None, None]    # the search that read the slot finished
+        self._downloaded: list[torch.cuda.Event | None] = [None, None]  # D2H of the slot's result finished
+        self._keep: list[tuple | None] = [None, None]                    # device results until their D2H is done
+
+    def _upload(self, slot: int, hb: Tensor) -> None:
         if hb.ndim != 2 or hb.device.type != "cpu":
             raise ValueError("host batches must be 2-D CPU tensors (pin them for asynchronous copies)")
         n = hb.shape[0]
-        buf = q_dev[slot]
+        buf = self._q_dev[slot]
         if buf is None or buf.shape[0] < n or buf.shape[1] != hb.shape[1] or buf.dtype != hb.dtype:
-            if searched[slot] is not None:
-                searched[slot].synchronize()  # the old buffer is released: its last reader must be done
-            q_dev[slot] = torch.empty((n, hb.shape[1]), dtype=hb.dtype, device=dev)
-        with torch.cuda.stream(copy):
-            if searched[slot] is not None:
-                copy.wait_event(searched[slot])  # the search that last read this device buffer
-            q_dev[slot][:n].copy_(hb, non_blocking=True)
+            if self._searched[slot] is not None:
+                self._searched[slot].synchronize()  # the old buffer is released: its last reader must be done
+            self._q_dev[slot] = torch.empty((n, hb.shape[1]), dtype=hb.dtype, device=self.device)
+        with torch.cuda.stream(self._copy):
+            if self._searched[slot] is not None:
+                self._copy.wait_event(self._searched[slot])  # the search that last read this device buffer
+            self._q_dev[slot][:n].copy_(hb, non_blocking=True)
             ev = torch.cuda.Event()
-            ev.record(copy)
-        uploaded[slot] = ev
-        q_n[slot] = n
+            ev.record(self._copy)
+        self._uploaded[slot] = ev
+        self._q_n[slot] = n
 
-    def search(slot: int) -> None:
-        n = q_n[slot]
-        if out_s[slot] is None or out_s[slot].shape[0] < n:
-            out_s[slot] = torch.empty((n, k), dtype=torch.float32).pin_memory()
-            out_i[slot] = torch.empty((n, k), dtype=torch.int32).pin_memory()
-        compute.wait_event(uploaded[slot])
-        s, i = store.search_raw(q_dev[slot][:n], k)
+    def _search(self, slot: int, compute) -> None:
+        n, k = self._q_n[slot], self.k
+        if self._out_s[slot] is None or self._out_s[slot].shape[0] < n:
+            self._out_s[slot] = torch.empty((n, k), dtype=torch.float32).pin_memory()
+            self._out_i[slot] = torch.empty((n, k), dtype=torch.int32).pin_memory()
+        compute.wait_event(self._uploaded[slot])
+        s, i = self.store.search_raw(self._q_dev[slot][:n], k)
         ev = torch.cuda.Event()
         ev.record(compute)
-        searched[slot] = ev
-        keep[slot] = (s, i)
-        with torch.cuda.stream(copy):
-            copy.wait_event(ev)
-            out_s[slot][:n].copy_(s, non_blocking=True)
-            out_i[slot][:n].copy_(i, non_blocking=True)
+        self._searched[slot] = ev
+        self._keep[slot] = (s, i)
+        with torch.cuda.stream(self._copy):
+            self._copy.wait_event(ev)
+            self._out_s[slot][:n].copy_(s, non_blocking=True)
+            self._out_i[slot][:n].copy_(i, non_blocking=True)
             done = torch.cuda.Event()
-            done.record(copy)
-        downloaded[slot] = done
-        r_n[slot] = n
+            done.record(self._copy)
+        self._downloaded[slot] = done
+        self._r_n[slot] = n
 
-    def collect(slot: int) -> tuple[Tensor, Tensor]:
-        downloaded[slot].synchronize()
-        keep[slot] = None
-        return out_s[slot][: r_n[slot]], out_i[slot][: r_n[slot]]
+    def _collect(self, slot: int) -> tuple[Tensor, Tensor]:
+        self._downloaded[slot].synchronize()
+        self._keep[slot] = None
+        return self._out_s[slot][: self._r_n[slot]], self._out_i[slot][: self._r_n[slot]]
 
-    it = iter(host_batches)
-    try:
-        current = next(it, None)
-        if current is not None:
-            upload(0, current)
-        i = 0
-        waiting = None  # the slot whose result has not been yielded yet
-        while current is not None:
-            slot = i & 1
-            following = next(it, None)
-            if following is not None:
-                upload(slot ^ 1, following)  # in flight while this batch is searched
-            search(slot)                     # enqueued behind batch i - 1's search: no gap on the device
+    def run(self, host_batches):
+        compute = torch.cuda.current_stream(self.device)
+        it = iter(host_batches)
+        try:
+            current = next(it, None)
+            if current is not None:
+                self._upload(0, current)
+            i = 0
+            waiting = None  # the slot whose result has not been yielded yet
+            while current is not None:
+                slot = i & 1
+                following = next(it, None)
+                if following is not None:
+                    self._upload(slot ^ 1, following)  # in flight while this batch is searched
+                self._search(slot, compute)            # enqueued behind batch i - 1's search: no gap on the device
+                if waiting is not None:
+                    yield self._collect(waiting)       # batch i - 1: its host buffers are rewritten by batch i + 1
+                waiting = slot
+                current = following
+                i += 1
             if waiting is not None:
-                yield collect(waiting)       # batch i - 1: its host buffers are rewritten by batch i + 1
-            waiting = slot
-            current = following
-            i += 1
-        if waiting is not None:
-            yield collect(waiting)
-    finally:
-        copy.synchronize()  # nothing of ours is in flight when the buffers go back to the allocator
+                yield self._collect(waiting)
+        finally:
+            self._copy.synchronize()  # nothing of ours is in flight when the caller moves on
+
+
+def search_host_batches(store, host_batches, k: int):
+    """One-shot form of `HostBatchSearch(store, k).run(host_batches)`."""
+    yield from HostBatchSearch(store, k).run(host_batches)

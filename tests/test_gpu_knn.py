@@ -480,3 +480,8 @@ def test_search_host_batches_streams_ragged_batches():
     with pytest.raises(ValueError):
         list(S.search_host_batches(st, [torch.zeros(5)], 10))
     check(store, queries[:300], 10, got[0][0], got[0][1].to(torch.int64))
+    # a persistent streamer keeps its staging buffers across runs
+    hs = S.HostBatchSearch(st, 10)
+    for _ in range(2):
+        again = [(s_h.clone(), i_h.clone()) for s_h, i_h in hs.run(host)]
+        assert torch.equal(torch.cat([g[1] for g in again]), want_i.cpu())
