@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--pool", default="none")
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="exact")
+    ap.add_argument("--side", type=int, default=16, help="feature-map side for the l2norm case")
     a = ap.parse_args()
     peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
     dev = torch.device("cuda", 0)
@@ -70,11 +71,11 @@ def main():
     elif a.what == "l2norm":
         from imagescry_b200.models.embedding import l2_normalize_cells
 
-        B, E, h, w = a.batch, 1280, 16, 16
+        B, E, h, w = a.batch, 1280, a.side, a.side
         fmap = torch.randn((B, E, h, w), generator=g, device=dev)
         ts = timeit(lambda: l2_normalize_cells(fmap), a.iters, a.warm)
         gbs = fmap.numel() * 8 / (min(ts) * 1e-3) / 1e9
-        print(json.dumps({"case": f"l2norm B={B}", "ms": ts, "GBps": gbs, "frac_hbm": gbs / peaks["hbm_gbs"]}))
+        print(json.dumps({"case": f"l2norm B={B} {h}x{w}", "ms": ts, "GBps": gbs, "frac_hbm": gbs / peaks["hbm_gbs"]}))
     elif a.what == "graph":
         from imagescry_b200.search import EmbeddingStore
 
